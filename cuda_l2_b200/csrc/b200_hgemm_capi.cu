@@ -1,0 +1,124 @@
+// libb200_hgemm.so — C-ABI entry points declared in include/b200_hgemm.h.
+// Holds every kernel configuration and the per-shape dispatcher. No torch, no CUTLASS, no cuBLAS.
+#include "../../include/b200_hgemm.h"
+
+#include <atomic>
+
+#include "hgemm_configs.cuh"
+#include "hgemm_dispatch.cuh"
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+template <bool kAccF32>
+int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m, int max_ctas,
+               cudaStream_t s) {
+  using namespace b200;
+  int st;
+  switch (id) {
+#define B200_CASE(ID, BN, STAGES, CG)                                                              \
+  case ID:                                                                                         \
+    st = host::launch<Config<BN, STAGES, CG, kAccF32>>(A, Bt, C, M, N, K, s, group_m, max_ctas);   \
+    break;
+    B200_HGEMM_CONFIGS(B200_CASE)
+#undef B200_CASE
+    default:
+      return host::kBadConfig;
+  }
+  if (st == host::kOk) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return st;
+}
+
+int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m,
+        int max_ctas, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (acc_bits == 32) return run_config<true>(id, A, Bt, C, M, N, K, group_m, max_ctas, s);
+  if (acc_bits == 16) return run_config<false>(id, A, Bt, C, M, N, K, group_m, max_ctas, s);
+  return b200::host::kBadConfig;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_hgemm_num_configs(void) { return b200::kNumConfigs; }
+
+int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group) {
+  switch (config_id) {
+#define B200_CASE(ID, BN, STAGES, CG)  \
+  case ID:                             \
+    if (bn) *bn = BN;                  \
+    if (stages) *stages = STAGES;      \
+    if (cta_group) *cta_group = CG;    \
+    return 0;
+    B200_HGEMM_CONFIGS(B200_CASE)
+#undef B200_CASE
+    default:
+      return b200::host::kBadConfig;
+  }
+}
+
+int b200_hgemm_select_config(int acc_bits, int M, int N, int K) {
+  if (acc_bits != 32 && acc_bits != 16) return b200::host::kBadConfig;
+  if (M <= 0 || N <= 0 || K <= 0) return b200::host::kBadShape;
+  return b200::dispatch::select(acc_bits, M, N, K).config_id;
+}
+
+int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C, int M,
+                          int N, int K, int group_m, int max_ctas, void* stream) {
+  return run(acc_bits, config_id, A, B_kmajor, C, M, N, K, group_m, max_ctas, stream);
+}
+
+int b200_hgemm_f32acc(const void* A, const void* /*B_rowmajor*/, const void* B_kmajor, void* C, int M, int N,
+                      int K, void* stream) {
+  int st = b200::host::validate(A, B_kmajor, C, M, N, K);
+  if (st) return st;
+  const b200::dispatch::Choice ch = b200::dispatch::select(32, M, N, K);
+  return run(32, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, stream);
+}
+
+int b200_hgemm_f16acc(const void* A, const void* /*B_rowmajor*/, const void* B_kmajor, void* C, int M, int N,
+                      int K, void* stream) {
+  int st = b200::host::validate(A, B_kmajor, C, M, N, K);
+  if (st) return st;
+  const b200::dispatch::Choice ch = b200::dispatch::select(16, M, N, K);
+  return run(16, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, stream);
+}
+
+int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* hC, int M, int N, int K) {
+  if (!hA || !hB_kmajor || !hC) return b200::host::kNullPointer;
+  if (M <= 0 || N <= 0 || K <= 0) return b200::host::kBadShape;
+  // device scratch grows monotonically and is reused across calls
+  static thread_local void* dbuf = nullptr;
+  static thread_local size_t dcap = 0;
+  const size_t a_bytes = size_t(M) * K * 2, b_bytes = size_t(N) * K * 2, c_bytes = size_t(M) * N * 2;
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t need = up(a_bytes) + up(b_bytes) + up(c_bytes);
+  if (need > dcap) {
+    if (dbuf) cudaFree(dbuf);
+    dbuf = nullptr; dcap = 0;
+    cudaError_t e = cudaMalloc(&dbuf, need);
+    if (e != cudaSuccess) return int(e);
+    dcap = need;
+  }
+  char* dA = static_cast<char*>(dbuf);
+  char* dB = dA + up(a_bytes);
+  char* dC = dB + up(b_bytes);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(dA, hA, a_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess) return int(e);
+  if ((e = cudaMemcpyAsync(dB, hB_kmajor, b_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess) return int(e);
+  int st = (acc_bits == 32)   ? b200_hgemm_f32acc(dA, nullptr, dB, dC, M, N, K, nullptr)
+           : (acc_bits == 16) ? b200_hgemm_f16acc(dA, nullptr, dB, dC, M, N, K, nullptr)
+                              : int(b200::host::kBadConfig);
+  if (st) return st;
+  if ((e = cudaMemcpyAsync(hC, dC, c_bytes, cudaMemcpyDeviceToHost, 0)) != cudaSuccess) return int(e);
+  e = cudaStreamSynchronize(0);
+  return e == cudaSuccess ? 0 : int(e);
+}
+
+unsigned long long b200_hgemm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* b200_hgemm_strerror(int status) { return b200::host::status_string(status); }
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+// B200 (sm_100a) HGEMM:  C[M,N] (fp16) = A[M,K] (fp16, K-contiguous) * Bt[N,K]^T (fp16, K-contiguous)
+// with fp32 (F32F16F16F32) or fp16 (F16F16F16F16) accumulation in tensor memory.
+//
+// Replaces, for --device_type b200, the per-shape kernels the reference ships for older GPUs
+// (reference: kernels/a100_F32F16F16F32/4096_4096_4096.cu:22-177 mainloop+epilogue, :179-279 launcher;
+//  kernels/h100_F32F16F16F32/4096_4096_4096.cu:21-80 for the TMA/wgmma flavour). Same contract:
+// TN operands (A row-major, B supplied K-major as `b_col_major`, tools/utils.py:110-115), C row-major
+// fully overwritten, one round-to-nearest fp32->fp16 conversion at the end.
+//
+// Design (nothing below is translated from the reference; it is written for Blackwell):
+//   * persistent CTAs (one per SM, or one CTA pair per 2 SMs), static tile schedule with grouped
+//     rasterisation for L2 reuse;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread),
+//     warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> swizzled smem -> TMA store);
+//   * operands land in 128B-swizzled smem via cp.async.bulk.tensor (OOB rows/cols zero-filled, so no
+//     harness padding is ever needed), consumed in place by tcgen05.mma through smem descriptors;
+//   * kStages-deep full/empty mbarrier ring between TMA and MMA, and a 2-deep TMEM accumulator ring
+//     between MMA and epilogue so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * kCtaGroup == 2: cta_group::2 MMA (256 x BN per CTA pair), each CTA loads its 128 rows of A and
+//     half of the B tile, the leader CTA issues the MMAs and multicasts the commit to both CTAs.
+#pragma once
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace b200 {
+
+constexpr int kBlockK = 64;          // 64 fp16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;           // K per tcgen05.mma.kind::f16
+constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
+constexpr int kNumThreads = 256;     // 8 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiChunkN = 64;       // columns per epilogue step (128 B of fp16 = one swizzle row)
+constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_>
+struct Config {
+  static constexpr int BN = BN_;               // tile N (= UMMA N)
+  static constexpr int STAGES = STAGES_;
+  static constexpr int CTA_GROUP = CTA_GROUP_; // 1: 128xBN per CTA; 2: 256xBN per CTA pair
+  static constexpr bool ACC_F32 = ACC_F32_;
+  static constexpr int TILE_M = kBlockM * CTA_GROUP;
+  static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA loads per stage
+  static constexpr int A_STAGE_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int EPI_BUF_BYTES = 32 * kEpiChunkN * 2;  // one warp, one chunk: 32 rows x 128 B
+  static constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;    // 4 warps x double buffer
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS_USED = kAccStages * BN;
+  static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
+                                 : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
+  static_assert(BN % kEpiChunkN == 0 && BN >= 64 && BN <= 256, "tile N must be a multiple of 64, <= 256");
+  static_assert(LOAD_N % 8 == 0 && (BN % 16) == 0, "UMMA N constraints");
+  static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
+};
+
+// 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
+// [4,6) D fmt (0=f16,1=f32) | [7,10) A fmt (0=f16) | [10,13) B fmt | [15] A major | [16] B major
+// | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool acc_f32) {
+  return (acc_f32 ? 1u : 0u) << 4 | (uint32_t(umma_n >> 3) << 17) | (uint32_t(umma_m >> 4) << 24);
+}
+
+// 64-bit shared-memory matrix descriptor: K-major tile, 128B swizzle, rows 128 B apart,
+// 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major, version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;   // SWIZZLE_128B
+  return d;
+}
+
+struct TileCoord { int m_blk, n_blk; };
+
+// Grouped rasterisation: walk `group_m` row-blocks down before stepping one column-block right,
+// so a wave of CTAs shares a compact set of A/B panels in L2.
+__device__ __forceinline__ TileCoord tile_coord(int t, int num_m_blocks, int num_n_blocks, int group_m) {
+  const int tiles_per_group = group_m * num_n_blocks;
+  const int group = t / tiles_per_group;
+  const int first_m = group * group_m;
+  const int gsz = min(group_m, num_m_blocks - first_m);
+  const int in_group = t - group * tiles_per_group;
+  TileCoord c;
+  c.m_blk = first_m + in_group % gsz;
+  c.n_blk = in_group / gsz;
+  return c;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kNumThreads, 1)
+hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, 128}
+                const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, LOAD_N}
+                const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {64, 32}
+                int M, int N, int K, int group_m) {
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CG = Cfg::CTA_GROUP;
+  using namespace ptx;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + STAGES * Cfg::A_STAGE_BYTES;
+  const uint32_t smem_epi = smem_b + STAGES * Cfg::B_STAGE_BYTES;
+  const uint32_t smem_bar = smem_epi + Cfg::EPI_BYTES;
+  const uint32_t bar_full = smem_bar;                        // [STAGES]
+  const uint32_t bar_empty = bar_full + 8 * STAGES;          // [STAGES]
+  const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;     // [kAccStages]
+  const uint32_t bar_tmem_empty = bar_tmem_full + 8 * kAccStages;
+  const uint32_t tmem_slot = bar_tmem_empty + 8 * kAccStages;
+  static_assert(8 * (2 * STAGES + 2 * kAccStages) + 4 <= Cfg::BAR_BYTES, "barrier block too small");
+
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  const int num_m_blocks = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  const int num_n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int num_workers = gridDim.x / CG;       // CTAs (CG=1) or CTA pairs (CG=2)
+  const int worker = blockIdx.x / CG;
+
+  // ------------------------------------------------------------------ one-time setup
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);    // producer's arrive.expect_tx (leader CTA's only, for a pair)
+      mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
+      mbar_init(bar_tmem_empty + 8 * a, 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish<CG>();
+  }
+  __syncwarp();   // reconverge after the elected-lane branches before the aligned barrier
+  tc_fence_before_sync();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // ------------------------------------------------------------------ roles
+  if (warp == 0) {
+    // ===== TMA producer (one thread) =====
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
+      const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
+        const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM;
+        const int n0 = tc.n_blk * BN + int(cta_rank) * Cfg::LOAD_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
+          const uint32_t fb = full0 + 8 * stage;
+          tma_load_2d<CG>(smem_a + stage * Cfg::A_STAGE_BYTES, &tmap_a, fb, kb * kBlockK, m0);
+          tma_load_2d<CG>(smem_b + stage * Cfg::B_STAGE_BYTES, &tmap_b, fb, kb * kBlockK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread of the leader CTA) =====
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = worker; t < num_tiles; t += num_workers) {
+        mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after_sync();
+          const uint64_t da = make_smem_desc(smem_a + stage * Cfg::A_STAGE_BYTES);
+          const uint64_t db = make_smem_desc(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 B per K step inside the 128 B swizzle row == +2 in the (addr >> 4) field
+            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          // free the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
+          else umma_commit<CG>(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
+        else umma_commit<CG>(bar_tmem_full + 8 * acc);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
+    const int q = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32q, 32q+32)
+    const uint32_t epi_buf0 = smem_epi + q * (2 * Cfg::EPI_BUF_BYTES);
+    const uint32_t tmem_empty0 = (CG == 2) ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
+    const uint32_t row_off = uint32_t(lane) * 128u;
+    const uint32_t sw = uint32_t(lane & 7);
+    int acc = 0; uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int t = worker; t < num_tiles; t += num_workers) {
+      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
+      const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM + q * 32;
+      const int n0 = tc.n_blk * BN;
+      mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
+#pragma unroll
+      for (int j = 0; j < BN / kEpiChunkN; ++j) {
+        uint32_t packed[32];
+        if constexpr (Cfg::ACC_F32) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(taddr0 + j * kEpiChunkN, v0);
+          tmem_ld_32x32b_x32(taddr0 + j * kEpiChunkN + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            packed[i] = pack_f16x2_rn(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+            packed[16 + i] = pack_f16x2_rn(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          }
+        } else {
+          tmem_ld_32x32b_x32_pack16(taddr0 + j * kEpiChunkN, packed);
+          tmem_ld_wait();
+        }
+        if (j == BN / kEpiChunkN - 1) {
+          // whole accumulator is in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
+            else mbar_arrive(tmem_empty0 + 8 * acc);
+          }
+        }
+        // the store that last used this staging buffer must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t dst = epi_buf0 + buf * Cfg::EPI_BUF_BYTES + row_off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1],
+                       packed[4 * c + 2], packed[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int nc = n0 + j * kEpiChunkN;
+          if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
+            tma_store_2d(&tmap_c, epi_buf0 + buf * Cfg::EPI_BUF_BYTES, nc, m0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  // ------------------------------------------------------------------ teardown
+  __syncwarp();   // single-lane roles rejoin their warp before the aligned barrier
+  tc_fence_before_sync();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace b200
