@@ -65,6 +65,15 @@ int b200_hgemm_select_config(int acc_bits, int M, int N, int K) {
   return b200::dispatch::select(acc_bits, M, N, K).config_id;
 }
 
+int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m) {
+  if (acc_bits != 32 && acc_bits != 16) return b200::host::kBadConfig;
+  if (M <= 0 || N <= 0 || K <= 0) return b200::host::kBadShape;
+  const b200::dispatch::Choice ch = b200::dispatch::select(acc_bits, M, N, K);
+  if (config_id) *config_id = ch.config_id;
+  if (group_m) *group_m = ch.group_m;
+  return 0;
+}
+
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C, int M,
                           int N, int K, int group_m, int max_ctas, void* stream) {
   return run(acc_bits, config_id, A, B_kmajor, C, M, N, K, group_m, max_ctas, stream);

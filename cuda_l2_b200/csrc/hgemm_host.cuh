@@ -85,7 +85,8 @@ struct MapCache {
   CUtensorMap maps[kSlots];
   bool valid[kSlots];
   MapCache() { std::memset(valid, 0, sizeof(valid)); }
-  int get(const void* ptr, int rows, int cols, int box_rows, const CUtensorMap** out) {
+  // Copies the map out: two operands of one call may share a slot, so a pointer into the cache would alias.
+  int get(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
     MapKey k{ptr, rows, cols, box_rows};
     uint64_t h = (reinterpret_cast<uint64_t>(ptr) >> 8) * 0x9E3779B97F4A7C15ull;
     h ^= uint64_t(uint32_t(rows)) * 0xC2B2AE3D27D4EB4Full + uint64_t(uint32_t(cols)) * 0x165667B19E3779F9ull +
@@ -97,7 +98,7 @@ struct MapCache {
       keys[slot] = k;
       valid[slot] = true;
     }
-    *out = &maps[slot];
+    std::memcpy(out, &maps[slot], sizeof(CUtensorMap));
     return kOk;
   }
 };
@@ -148,7 +149,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     attr_dev = di.dev;
   }
 
-  const CUtensorMap *ma, *mb, *mc;
+  CUtensorMap ma, mb, mc;
   MapCache& cache = map_cache();
   if ((st = cache.get(A, M, K, kBlockM, &ma)) != kOk) return st;
   if ((st = cache.get(Bt, N, K, Cfg::LOAD_N, &mb)) != kOk) return st;
@@ -174,7 +175,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (Cfg::CTA_GROUP > 1) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, *ma, *mb, *mc, M, N, K, group_m);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m);
   return e == cudaSuccess ? kOk : int(e);
 }
 

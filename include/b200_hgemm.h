@@ -46,6 +46,8 @@ int b200_hgemm_num_configs(void);
 int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group);
 /* The configuration the dispatcher uses for this problem (acc_bits = 32 or 16). */
 int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
+/* Same, also reporting the rasterisation group (0 = kernel default). Returns 0 or a negative status. */
+int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m);
 /* Run one explicit configuration. group_m <= 0 and max_ctas <= 0 select the defaults. */
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C,
                           int M, int N, int K, int group_m, int max_ctas, void* stream);
