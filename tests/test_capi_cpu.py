@@ -1,0 +1,68 @@
+"""The C-ABI libraries load and export every symbol include/*.h declares (no compute without a GPU)."""
+import ctypes
+import re
+
+import pytest
+
+from conftest import REPO
+from cuda_l2_b200 import capi
+
+DECL = re.compile(r"^\s*(?:const\s+)?(?:unsigned\s+long\s+long|int|void|char\s*\*|const\s+char\s*\*)\s*\*?\s*(b200_\w+)\s*\(", re.M)
+
+
+def declared(header: str) -> list[str]:
+    return sorted(set(DECL.findall((REPO / "include" / header).read_text())))
+
+
+def test_headers_and_python_binding_agree():
+    assert declared("b200_hgemm.h") == sorted(capi.exported_symbols()["libb200_hgemm.so"])
+    assert declared("b200_baselines.h") == sorted(capi.exported_symbols()["libb200_baselines.so"])
+
+
+def test_libraries_export_every_declared_symbol(built_libs):
+    for header, path in (("b200_hgemm.h", built_libs["capi"]), ("b200_baselines.h", built_libs["baselines"])):
+        lib = ctypes.CDLL(str(path))
+        for sym in declared(header):
+            assert hasattr(lib, sym), f"{path.name} does not export {sym}"
+
+
+def test_config_table_and_dispatch(built_libs):
+    cfgs = capi.configs()
+    assert len(cfgs) >= 5
+    for c in cfgs:
+        assert c["bn"] % 64 == 0 and 64 <= c["bn"] <= 256 and c["cta_group"] in (1, 2) and c["stages"] >= 2
+        smem = 1024 + c["stages"] * (128 * 64 * 2 + (c["bn"] // c["cta_group"]) * 64 * 2) + 32768 + 256
+        assert smem <= 232448
+    ids = {c["id"] for c in cfgs}
+    for acc in ("fp32", "fp16"):
+        for mnk in ((64, 4096, 64), (4096, 4096, 4096), (8192, 8192, 8192), (2048, 11008, 4096), (64, 64, 64),
+                    (16384, 16384, 16384), (200, 328, 72)):
+            cid, gm = capi.select(acc, *mnk)
+            assert cid in ids and gm >= 0
+            if mnk[0] <= 128:
+                assert cfgs[cid]["cta_group"] == 1     # a CTA pair would waste its second half on padding
+
+
+def test_argument_validation_happens_before_any_cuda_call(built_libs):
+    lib = capi.hgemm_lib()
+    assert lib.b200_hgemm_f32acc(None, None, None, None, 64, 64, 64, None) == -5       # null pointers
+    buf = ctypes.create_string_buffer(1 << 16)
+    p = ctypes.addressof(buf)
+    p = (p + 15) & ~15
+    assert lib.b200_hgemm_f32acc(p, None, p, p, 0, 64, 64, None) == -1                  # bad shape
+    assert lib.b200_hgemm_f16acc(p, None, p, p, 64, 64, 60, None) == -2                 # K % 8 != 0
+    assert lib.b200_hgemm_f16acc(p, None, p, p, 64, 60, 64, None) == -2                 # N % 8 != 0
+    assert lib.b200_hgemm_f32acc(p + 2, None, p, p, 64, 64, 64, None) == -2             # misaligned A
+    assert lib.b200_hgemm_run_config(32, 99, p, p, p, 64, 64, 64, 0, 0, None) == -6     # unknown config
+    assert lib.b200_hgemm_run_config(8, 0, p, p, p, 64, 64, 64, 0, 0, None) == -6       # unknown accumulator
+    assert "16-byte" in capi.strerror(-2)
+    assert capi.launch_count() == 0
+
+
+def test_python_binding_rejects_cpu_tensors(built_libs):
+    import torch
+    a = torch.zeros(64, 64, dtype=torch.half)
+    with pytest.raises(capi.B200HgemmError):
+        capi.hgemm(a, a, a)          # CPU tensors: there is no CPU fallback
+    with pytest.raises(capi.B200HgemmError):
+        capi.hgemm(a.float(), a, a)

@@ -1,0 +1,166 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle — the tests proper, run on the B200.
+
+Bars: BIT-EXACT against the oracle / golden truth on the reference's test domain (0/1 operands, entries with
+|truth| <= 2047; reference zero_one_correctness_check.py:92,169-172); on N(0,1) operands — where the reference
+pins nothing — within  |err| <= 2^-10 |truth| + 2^-10 * sqrt(K) * 0.05 + 1e-3  for fp32 accumulation (one fp16
+rounding plus summation-order noise) and a 16x looser bound for fp16 accumulation.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cuda_l2_b200 import capi
+from cuda_l2_b200.harness import correctness as zc
+from cuda_l2_b200.harness.common import Padding
+
+pytestmark = pytest.mark.gpu
+ACCS = ("fp32", "fp16")
+
+
+def dev(x: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def run(a: torch.Tensor, bt: torch.Tensor, acc: str, cfg=None, **kw) -> torch.Tensor:
+    """a [M,K], bt [N,K] (K-major B) device tensors -> C [M,N] through libb200_hgemm.so."""
+    m, n = a.shape[0], bt.shape[0]
+    c = torch.full((m, n), float("nan"), dtype=torch.half, device="cuda")
+    b_col_major = bt.reshape(bt.shape[1], bt.shape[0])     # labelled [K,N], storage [N,K] (as_col_major's output)
+    if cfg is None:
+        capi.hgemm(a, b_col_major, c, acc)
+    else:
+        capi.hgemm_config(a, b_col_major, c, cfg, acc, **kw)
+    torch.cuda.synchronize()
+    return c
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_b200(built_libs):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert torch.cuda.get_device_capability()[0] == 10, "these kernels are sm_100a only"
+    before = capi.launch_count()
+    yield
+    assert capi.launch_count() > before, "no kernel of libb200_hgemm.so was launched"
+
+
+@pytest.mark.parametrize("acc", ACCS)
+def test_golden_zero_one_vectors_bit_exact(zero_one_cases, acc):
+    for c in zero_one_cases:
+        if c["k"] % 8 or c["n"] % 8:
+            continue
+        got = run(dev(c["a"]), dev(c["b"].T), acc).cpu().numpy()
+        truth = c["truth"]
+        keep = np.abs(truth.astype(np.float32)) <= 2047
+        assert np.array_equal(got[keep], truth[keep]), (acc, c["m"], c["n"], c["k"])
+        d, _, n_bad = oracle.zero_one_max_diff(got, truth)
+        assert d == 0.0 and n_bad == 0
+        if acc == "fp32":      # fp32 accumulation is exact far beyond the mask: every entry must agree
+            assert np.array_equal(got.view(np.uint16), truth.view(np.uint16))
+
+
+@pytest.mark.parametrize("acc", ACCS)
+def test_every_configuration_matches_the_oracle(acc):
+    shapes = [(128, 64, 64), (256, 256, 64), (200, 328, 72), (512, 768, 512), (1000, 1000, 1000), (64, 4096, 64)]
+    for cfg in capi.configs():
+        for (m, n, k) in shapes:
+            a = oracle.fill_zero_one((m, k), 2, seed=m * 7 + cfg["id"])
+            bt = oracle.fill_zero_one((n, k), 2, seed=n * 13 + k)
+            want = oracle.hgemm_f32acc(a, bt, fast=True)
+            got = run(dev(a), dev(bt), acc, cfg=cfg["id"]).cpu().numpy()
+            assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (acc, cfg, m, n, k)
+
+
+@pytest.mark.parametrize("acc", ACCS)
+@pytest.mark.parametrize("group_m,max_ctas", [(1, 0), (3, 0), (64, 0), (0, 8), (0, 37)])
+def test_schedule_knobs_do_not_change_results(acc, group_m, max_ctas):
+    m, n, k = 1536, 1280, 256
+    a, bt = oracle.fill_zero_one((m, k), 2, 1), oracle.fill_zero_one((n, k), 2, 2)
+    want = oracle.hgemm_f32acc(a, bt, fast=True)
+    for cfg in capi.configs():
+        got = run(dev(a), dev(bt), acc, cfg=cfg["id"], group_m=group_m, max_ctas=max_ctas).cpu().numpy()
+        assert np.array_equal(got, want), (cfg, group_m, max_ctas)
+
+
+@pytest.mark.parametrize("acc", ACCS)
+def test_randn_golden_within_stated_tolerance(randn_cases, acc):
+    loosen = 1.0 if acc == "fp32" else 16.0
+    for c in randn_cases:
+        got = run(dev(c["a"]), dev(c["b"].T), acc).cpu().numpy().astype(np.float32)
+        truth = c["truth"].astype(np.float32)
+        tol = loosen * (2.0**-10 * np.abs(truth) + 2.0**-10 * np.sqrt(c["k"]) * 0.05 + 1e-3)
+        assert (np.abs(got - truth) <= tol).all(), (acc, c["m"], c["n"], c["k"], float(np.abs(got - truth).max()))
+
+
+@pytest.mark.parametrize("acc", ACCS)
+def test_guard_bands_untouched_and_c_fully_overwritten(acc):
+    # the reference's OOB-write probe (zero_one_correctness_check.py:101-150) on ragged and tile-aligned shapes
+    for (m, n, k) in [(200, 328, 72), (128, 256, 64), (1000, 1000, 1000), (64, 4096, 64)]:
+        ga, gbt, gc = zc.GuardedOperand(m, k, "cuda"), zc.GuardedOperand(n, k, "cuda"), zc.GuardedOperand(m, n, "cuda")
+        ga.view.copy_(dev(oracle.fill_zero_one((m, k), 2, 3)))
+        gbt.view.copy_(dev(oracle.fill_zero_one((n, k), 2, 4)))
+        gc.view.fill_(float("nan"))
+        capi.hgemm(ga.view, gbt.view.reshape(k, n), gc.view, acc)
+        torch.cuda.synchronize()
+        assert ga.bands_intact() and gbt.bands_intact() and gc.bands_intact()
+        assert not torch.isnan(gc.view).any()
+        want = oracle.hgemm_f32acc(ga.view.cpu().numpy(), gbt.view.cpu().numpy(), fast=True)
+        assert np.array_equal(gc.view.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("acc,mnk", [("fp32", (4096, 4096, 4096)), ("fp16", (8192, 8192, 8192)),
+                                     ("fp32", (2048, 11008, 4096)), ("fp32", (64, 4096, 64)), ("fp16", (64, 4096, 64))])
+def test_baseline_configs_pass_the_reference_check_procedure(acc, mnk):
+    """BASELINE.json configs at FULL size through the harness's own 0/1 procedure (CPU fp32 truth, mask, guard
+    bands, == 0 rule), with the C-ABI call in the kernel slot."""
+    name = f"cuda_l2_b200_{acc}"
+
+    def kernel(a, b, b_col_major, c):
+        capi.hgemm(a, b_col_major, c, acc)
+    kernel.__name__ = name
+    m, n, k = mnk
+    res = zc.run_zero_one_check(kernel_funcs=[torch.matmul, kernel], kernel_under_test_name=name, m=m, n=n, k=k,
+                                padding=Padding(), device="cuda", num_iterations=2, max_seconds=120,
+                                generator=torch.Generator(device="cuda").manual_seed(0))
+    assert res.success, res.message
+
+
+@pytest.mark.parametrize("acc", ACCS)
+def test_size_independent_properties_at_full_size(acc):
+    """Properties that need no CPU reference, at 8192-class sizes: identity, exact power-of-two scaling,
+    row-block decomposition, row-sum against a ones matrix."""
+    n = k = 4096
+    m = 8192
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = (torch.randint(0, 3, (m, k), device="cuda", generator=g) - 1).half()         # {-1, 0, 1}
+    eye_t = torch.eye(n, dtype=torch.half, device="cuda")                              # Bt = I  -> C = A
+    assert torch.equal(run(a, eye_t, acc), a)
+    bt = (torch.randint(0, 3, (n, k), device="cuda", generator=g) - 1).half()
+    c = run(a, bt, acc)
+    assert torch.equal(run(a * 2, bt, acc), c * 2)                                     # scaling by 2 is exact
+    assert torch.equal(run(a[1024:3072].contiguous(), bt, acc), c[1024:3072])          # rows are independent
+    ones_t = torch.ones((64, k), dtype=torch.half, device="cuda")
+    small = (torch.rand((m, k), device="cuda", generator=g) < 0.25).half()            # row sums ~1024 < 2048: exact
+    rs = run(small, ones_t, acc)
+    assert torch.equal(rs[:, 0].float(), small.float().sum(dim=1))
+    assert torch.equal(rs, rs[:, :1].expand(-1, 64))
+
+
+def test_host_buffer_entry_point_round_trips():
+    m, n, k = 512, 768, 256
+    a = torch.from_numpy(oracle.fill_zero_one((m, k), 2, 5)).pin_memory()
+    bt = torch.from_numpy(oracle.fill_zero_one((n, k), 2, 6)).pin_memory()
+    c = torch.empty((m, n), dtype=torch.half).pin_memory()
+    capi.hgemm_host(a, bt.reshape(k, n), c, "fp32")
+    assert np.array_equal(c.numpy(), oracle.hgemm_f32acc(a.numpy(), bt.numpy(), fast=True))
+
+
+def test_errors_are_loud():
+    a = torch.zeros((64, 60), dtype=torch.half, device="cuda")       # K % 8 != 0
+    with pytest.raises(capi.B200HgemmError):
+        capi.hgemm(a, torch.zeros((60, 64), dtype=torch.half, device="cuda"),
+                   torch.zeros((64, 64), dtype=torch.half, device="cuda"))
+    with pytest.raises(capi.B200HgemmError):                           # shape mismatch
+        capi.hgemm(torch.zeros((64, 64), dtype=torch.half, device="cuda"),
+                   torch.zeros((32, 64), dtype=torch.half, device="cuda"),
+                   torch.zeros((64, 64), dtype=torch.half, device="cuda"))

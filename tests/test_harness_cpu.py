@@ -1,0 +1,150 @@
+"""Host-side harness logic that needs no GPU: build glue, padding rule, 0/1 check plumbing, summary, CLI."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import GOLDEN, REPO
+from cuda_l2_b200.harness import correctness as zc
+from cuda_l2_b200.harness.common import Padding, kernel_func_name, padding_for, parse_mnk
+from tools import utils
+
+
+@pytest.fixture(scope="module")
+def helpers():
+    return json.loads((GOLDEN / "helpers.json").read_text())
+
+
+def test_extract_bm_bk_bn_matches_reference_outputs(helpers):
+    for name, text in helpers["snippets"].items():
+        assert list(utils.extract_bm_bk_bn(text)) == helpers["extract_bm_bk_bn"][name], name
+
+
+def test_as_col_major_matches_reference_outputs(helpers):
+    for case in helpers["as_col_major"]:
+        x = torch.arange(case["rows"] * case["cols"], dtype=torch.float32).reshape(case["rows"], case["cols"]).half()
+        y = utils.as_col_major(x)
+        assert list(y.shape) == case["shape_out"] and y.is_contiguous() == case["contiguous"]
+        assert y.flatten().tolist() == case["flat_out"]
+        # storage is the transpose, K-major
+        assert torch.equal(y.reshape(case["cols"], case["rows"]), x.t())
+
+
+def test_build_sources_layout():
+    src = utils.get_build_sources("4096_4096_4096", "fp32", "b200")
+    assert src == ["cublas/fp32/hgemm_cublas.cu", "cublas/fp32/hgemm_cublaslt_heuristic.cu",
+                   "cublas/fp32/hgemm_cublaslt_auto_tuning.cu", "kernels/b200_F32F16F16F32/4096_4096_4096.cu",
+                   "pybind/hgemm_b200_fp32.cc"]
+    assert utils.get_build_sources("64_64_64", "fp16", "b200")[3] == "kernels/b200_F16F16F16F16/64_64_64.cu"
+    for s in src:
+        assert (REPO / s).exists(), s
+    with pytest.raises(ValueError):
+        utils.get_build_sources("64_64_64", "bf16", "b200")
+    assert any("compute_100a" in f for f in utils.get_build_cuda_cflags())
+
+
+def test_kernel_tree_is_complete_and_needs_no_padding():
+    grid = (64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384)
+    for d in ("b200_F32F16F16F32", "b200_F16F16F16F16"):
+        files = {p.name for p in (REPO / "kernels" / d).glob("*.cu")}
+        assert len(files) == 1001
+        for m in grid:
+            assert f"{m}_{grid[3]}_{grid[-1]}.cu" in files
+        assert "2048_11008_4096.cu" in files
+    assert padding_for("4096_4096_4096", "fp32", "b200") == Padding(0, 0, 0)
+    assert padding_for("64_4096_64", "fp16", "b200") == Padding(0, 0, 0)
+
+
+def test_padding_rule_with_declared_tiles(tmp_path, monkeypatch):
+    # a source that DOES declare tiles gets the reference's padding (benchmarking_offline.py:107-112)
+    d = tmp_path / "kernels" / "b200_F32F16F16F32"
+    d.mkdir(parents=True)
+    (d / "4096_4096_4096.cu").write_text("auto BM = Int<160>{}; \nauto BN = Int<128>{};\nauto BK = Int<32>{};\n")
+    import cuda_l2_b200.harness.common as common
+    monkeypatch.setattr(common, "PROJECT_DIR", tmp_path)
+    assert common.padding_for("4096_4096_4096", "fp32", "b200") == Padding(m=64, k=0, n=0)
+
+
+def test_parse_and_names():
+    assert parse_mnk("2048_11008_4096") == (2048, 11008, 4096)
+    for bad in ("1_2", "a_b_c", "0_1_1"):
+        with pytest.raises(ValueError):
+            parse_mnk(bad)
+    assert kernel_func_name("b200", "fp16") == "cuda_l2_b200_fp16"
+
+
+def test_zero_one_plumbing_passes_and_catches_faults():
+    name = "cuda_l2_b200_fp32"
+    good = zc.cpu_stand_in(name)
+    g = torch.Generator().manual_seed(0)
+    res = zc.run_zero_one_check(kernel_funcs=[torch.matmul, good], kernel_under_test_name=name, m=64, n=256, k=64,
+                                padding=Padding(), device="cpu", num_iterations=3, generator=g)
+    assert res.success and res.result["iterations_run"] == 3 and res.result[f"avg_{name}_diff"] == 0.0
+
+    def off_by_one(a, b, bt, c):
+        good(a, b, bt, c)
+        c[0, 0] += 1
+    off_by_one.__name__ = name
+    res = zc.run_zero_one_check(kernel_funcs=[torch.matmul, off_by_one], kernel_under_test_name=name, m=64, n=64, k=64,
+                                padding=Padding(), device="cpu", num_iterations=2)
+    assert not res.success and "exceeds 0" in res.message
+
+    def scribbler(a, b, bt, c):          # writes one element past the end of C: guard band must notice
+        good(a, b, bt, c)
+        torch.tensor([], dtype=torch.half).set_(c.untyped_storage(), c.storage_offset() + c.numel(), (1,)).fill_(3.0)
+    scribbler.__name__ = name
+    res = zc.run_zero_one_check(kernel_funcs=[torch.matmul, scribbler], kernel_under_test_name=name, m=32, n=32, k=32,
+                                padding=Padding(), device="cpu", num_iterations=1)
+    assert not res.success and "overflow" in res.message
+
+    def nan_maker(a, b, bt, c):
+        good(a, b, bt, c)
+        c[1, 1] = float("nan")
+    nan_maker.__name__ = name
+    res = zc.run_zero_one_check(kernel_funcs=[torch.matmul, nan_maker], kernel_under_test_name=name, m=32, n=32, k=32,
+                                padding=Padding(), device="cpu", num_iterations=1)
+    assert not res.success
+
+
+def test_zero_one_mask_ignores_large_entries():
+    name = "cuda_l2_b200_fp16"
+
+    def saturating(a, b, bt, c):         # wrong only where |truth| > 2047 -> must still pass
+        zc.cpu_stand_in(name)(a, b, bt, c)
+        c[c > 2047] = 0
+    saturating.__name__ = name
+    res = zc.run_zero_one_check(kernel_funcs=[saturating], kernel_under_test_name=name, m=4, n=8, k=8192 * 2,
+                                padding=Padding(), device="cpu", num_iterations=1)
+    assert res.result["levels"] == 3 and res.success
+
+
+def test_cli_cpu_plumbing_exit_codes(tmp_path):
+    cmd = [sys.executable, str(REPO / "zero_one_correctness_check.py"), "--mnk", "64_4096_64", "--acc_precise", "fp32",
+           "--device_type", "b200", "--base_dir", str(tmp_path), "--gpu_device_id", "0", "--device", "cpu",
+           "--iterations", "2"]
+    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads((tmp_path / "zero_one_correctness_check_result.json").read_text())
+    assert out["success"] is True and out["result"]["m"] == 64 and out["result"]["n"] == 4096
+    bad = subprocess.run(cmd[:-6] + ["--device_type", "a100"], cwd=REPO, capture_output=True, text=True)
+    assert bad.returncode != 0      # unknown device type is rejected by argparse
+
+
+def test_summarize_result_picks_harder_layout(tmp_path):
+    import summarize_result as sr
+    ours = "cuda_l2_b200_fp32"
+    vals = {"hgemm_cublas_tn": (100.0, 120.0), "hgemm_cublas_nn": (90.0, 120.0),
+            "hgemm_cublaslt_heuristic_tn": (100.0, 90.0), "hgemm_cublaslt_heuristic_nn": (100.0, 95.0),
+            "hgemm_cublaslt_auto_tuning_tn": (110.0, 121.0), "hgemm_cublaslt_auto_tuning_nn": (100.0, 121.0),
+            "matmul": (80.0, 120.0)}
+    for name, (base, mine) in vals.items():
+        (tmp_path / f"benchmark_result_{name}.json").write_text(json.dumps({"records": {name: base, ours: mine}}))
+    rows = sr.summarize(str(tmp_path), "fp32", "b200")
+    assert rows["cuBLAS-max"]["Baseline TFLOPS"] == 100.0          # tn: speed-up 1.2 < nn 1.33 -> tn is harder
+    assert rows["cuBLASLt-heuristic-max"]["Speedup"] == pytest.approx(0.9)
+    assert rows["cuBLASLt-auto-tuning-max"]["Speedup"] == pytest.approx(1.1)
+    assert rows["torch.matmul"]["Speedup"] == pytest.approx(1.5)
+    assert sr.main(["--base_dir", str(tmp_path), "--acc_precise", "fp32", "--device_type", "b200"]) == 0
