@@ -274,7 +274,7 @@ def main():
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         achieved = flops_step / (ms_total / args.steps * 1e-3) * 1e-12      # per launch, from the CUDA events above
-        cfg_id, group_m = capi.select(args.acc, m, n, k)
+        cfg_id, group_m, splits = capi.select(args.acc, m, n, k)
         cfg = capi.configs()[cfg_id]
         traffic = None
         tf = REPO / "profiles" / "dram_traffic.json"
@@ -289,7 +289,7 @@ def main():
             "config": {"workload": f"{args.mnk} --acc_precise {args.acc} --mode offline", "parallelism": f"1 GEMM per GPU x {world}",
                        "l2_policy": f"rotating {nsets} operand sets ({nsets * set_bytes >> 20} MiB > 126 MiB L2)",
                        "kernel_config": {"tile": f"{128 * cfg['cta_group']}x{cfg['bn']}x64", "stages": cfg["stages"],
-                                         "cta_group": cfg["cta_group"], "group_m": group_m}},
+                                         "cta_group": cfg["cta_group"], "group_m": group_m, "split_k": splits}},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * (m * k + n * k),
                     "d2h_bytes_per_step": 2 * m * n, "steps": e2e_steps, "api": "b200_hgemm_host (pinned host buffers)"},
             "gpu_launches": launches,

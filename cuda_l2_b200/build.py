@@ -75,11 +75,12 @@ def build_baselines(verbose: bool = False, force: bool = False) -> Path:
 
 def build_dev_check(verbose: bool = False, force: bool = False) -> Path:
     lib = build_capi(verbose, force)
+    build_baselines(verbose, force)
     out = LIB_DIR / "dev_check"
     src = CSRC / "dev_check.cu"
     if force or _stale(out, [src, lib] + _headers()):
         _run([nvcc_path(), *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", "-o", str(out), str(src),
-              f"-L{LIB_DIR}", "-lb200_hgemm", "-lcublas", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], verbose)
+              f"-L{LIB_DIR}", "-lb200_hgemm", "-lb200_baselines", "-lcublas", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], verbose)
     return out
 
 

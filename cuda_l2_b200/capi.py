@@ -42,8 +42,8 @@ def hgemm_lib() -> ctypes.CDLL:
         lib.b200_hgemm_num_configs.restype = i
         lib.b200_hgemm_config_info.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_select_config.argtypes = [i, i, i, i]
-        lib.b200_hgemm_select.argtypes = [i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
-        lib.b200_hgemm_run_config.argtypes = [i, i, vp, vp, vp, i, i, i, i, i, vp]
+        lib.b200_hgemm_select.argtypes = [i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
+        lib.b200_hgemm_run_config.argtypes = [i, i, vp, vp, vp, i, i, i, i, i, i, vp]
         lib.b200_hgemm_host.argtypes = [i, vp, vp, vp, i, i, i]
         lib.b200_hgemm_launch_count.restype = ctypes.c_ulonglong
         lib.b200_hgemm_strerror.argtypes = [i]
@@ -120,10 +120,10 @@ def hgemm(a, b_col_major, c, acc: str | int = "fp32", stream: int | None = None)
 
 
 def hgemm_config(a, b_col_major, c, config_id: int, acc: str | int = "fp32", group_m: int = 0, max_ctas: int = 0,
-                 stream: int | None = None) -> None:
+                 splits: int = 1, stream: int | None = None) -> None:
     m, n, k = _shape_check(a, b_col_major, c)
     _check(hgemm_lib().b200_hgemm_run_config(ACC_BITS[acc], config_id, a.data_ptr(), b_col_major.data_ptr(),
-                                            c.data_ptr(), m, n, k, group_m, max_ctas, stream), "b200_hgemm_run_config")
+                                            c.data_ptr(), m, n, k, group_m, max_ctas, splits, stream), "b200_hgemm_run_config")
 
 
 def hgemm_host(a_host, b_col_major_host, c_host, acc: str | int = "fp32") -> None:
@@ -151,11 +151,12 @@ def select_config(acc: str | int, m: int, n: int, k: int) -> int:
     return hgemm_lib().b200_hgemm_select_config(ACC_BITS[acc], m, n, k)
 
 
-def select(acc: str | int, m: int, n: int, k: int) -> tuple[int, int]:
-    """(config id, rasterisation group) the dispatcher uses for this problem."""
-    cid, gm = ctypes.c_int(), ctypes.c_int()
-    _check(hgemm_lib().b200_hgemm_select(ACC_BITS[acc], m, n, k, ctypes.byref(cid), ctypes.byref(gm)), "b200_hgemm_select")
-    return cid.value, gm.value
+def select(acc: str | int, m: int, n: int, k: int) -> tuple[int, int, int]:
+    """(config id, rasterisation group, split-K factor) the dispatcher uses for this problem."""
+    cid, gm, sp = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(hgemm_lib().b200_hgemm_select(ACC_BITS[acc], m, n, k, ctypes.byref(cid), ctypes.byref(gm), ctypes.byref(sp)),
+           "b200_hgemm_select")
+    return cid.value, gm.value, sp.value
 
 
 def launch_count() -> int:

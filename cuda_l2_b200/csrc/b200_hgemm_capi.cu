@@ -13,13 +13,13 @@ std::atomic<unsigned long long> g_launches{0};
 
 template <bool kAccF32>
 int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m, int max_ctas,
-               cudaStream_t s) {
+               int splits, cudaStream_t s) {
   using namespace b200;
   int st;
   switch (id) {
 #define B200_CASE(ID, BN, STAGES, CG)                                                              \
   case ID:                                                                                         \
-    st = host::launch<Config<BN, STAGES, CG, kAccF32>>(A, Bt, C, M, N, K, s, group_m, max_ctas);   \
+    st = host::launch<Config<BN, STAGES, CG, kAccF32>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
     break;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
@@ -31,10 +31,10 @@ int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int
 }
 
 int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m,
-        int max_ctas, void* stream) {
+        int max_ctas, int splits, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (acc_bits == 32) return run_config<true>(id, A, Bt, C, M, N, K, group_m, max_ctas, s);
-  if (acc_bits == 16) return run_config<false>(id, A, Bt, C, M, N, K, group_m, max_ctas, s);
+  if (acc_bits == 32) return run_config<true>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
+  if (acc_bits == 16) return run_config<false>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
   return b200::host::kBadConfig;
 }
 
@@ -65,18 +65,19 @@ int b200_hgemm_select_config(int acc_bits, int M, int N, int K) {
   return b200::dispatch::select(acc_bits, M, N, K).config_id;
 }
 
-int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m) {
+int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m, int* splits) {
   if (acc_bits != 32 && acc_bits != 16) return b200::host::kBadConfig;
   if (M <= 0 || N <= 0 || K <= 0) return b200::host::kBadShape;
   const b200::dispatch::Choice ch = b200::dispatch::select(acc_bits, M, N, K);
   if (config_id) *config_id = ch.config_id;
   if (group_m) *group_m = ch.group_m;
+  if (splits) *splits = ch.splits;
   return 0;
 }
 
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C, int M,
-                          int N, int K, int group_m, int max_ctas, void* stream) {
-  return run(acc_bits, config_id, A, B_kmajor, C, M, N, K, group_m, max_ctas, stream);
+                          int N, int K, int group_m, int max_ctas, int splits, void* stream) {
+  return run(acc_bits, config_id, A, B_kmajor, C, M, N, K, group_m, max_ctas, splits, stream);
 }
 
 int b200_hgemm_f32acc(const void* A, const void* /*B_rowmajor*/, const void* B_kmajor, void* C, int M, int N,
@@ -84,7 +85,7 @@ int b200_hgemm_f32acc(const void* A, const void* /*B_rowmajor*/, const void* B_k
   int st = b200::host::validate(A, B_kmajor, C, M, N, K);
   if (st) return st;
   const b200::dispatch::Choice ch = b200::dispatch::select(32, M, N, K);
-  return run(32, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, stream);
+  return run(32, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, ch.splits, stream);
 }
 
 int b200_hgemm_f16acc(const void* A, const void* /*B_rowmajor*/, const void* B_kmajor, void* C, int M, int N,
@@ -92,7 +93,7 @@ int b200_hgemm_f16acc(const void* A, const void* /*B_rowmajor*/, const void* B_k
   int st = b200::host::validate(A, B_kmajor, C, M, N, K);
   if (st) return st;
   const b200::dispatch::Choice ch = b200::dispatch::select(16, M, N, K);
-  return run(16, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, stream);
+  return run(16, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, ch.splits, stream);
 }
 
 int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* hC, int M, int N, int K) {

@@ -1,8 +1,10 @@
 // dev_check — standalone bring-up / tuning tool for libb200_hgemm.so (developer tool, not product).
 //
-//   dev_check check <acc_bits> <cfg|-1> <M> <N> <K>          exactness vs an independent GPU checker
+//   dev_check check <acc_bits> <cfg|-1> <M> <N> <K> [gm splits]   exactness vs an independent GPU checker
 //   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters]  CUDA-event timing (+ cuBLAS for scale)
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
+//   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
+//   dev_check grid  <acc_bits> [part nparts budget_ms]       time every config on the whole shape grid (CSV)
 //
 // Inputs are small integers, so every product and partial sum is exact in fp16 and fp32: any
 // mismatch is a kernel bug, never rounding. C is surrounded by guard bands to catch stray writes.
@@ -12,11 +14,17 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <array>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
+#include "../../include/b200_baselines.h"
 #include "../../include/b200_hgemm.h"
+#include <chrono>
+#include <random>
 
 #define CK(x)                                                                              \
   do {                                                                                     \
@@ -101,14 +109,14 @@ static void cublas_tn(const Problem& p, __half* out) {
   if (s != CUBLAS_STATUS_SUCCESS) { printf("cublas error %d\n", int(s)); exit(3); }
 }
 
-static int run_ours(int acc, int cfg, const Problem& p, int group_m = 0) {
+static int run_ours(int acc, int cfg, const Problem& p, int group_m = 0, int splits = 1) {
   if (cfg < 0)
     return acc == 32 ? b200_hgemm_f32acc(p.A, nullptr, p.Bt, p.C, p.M, p.N, p.K, nullptr)
                      : b200_hgemm_f16acc(p.A, nullptr, p.Bt, p.C, p.M, p.N, p.K, nullptr);
-  return b200_hgemm_run_config(acc, cfg, p.A, p.Bt, p.C, p.M, p.N, p.K, group_m, 0, nullptr);
+  return b200_hgemm_run_config(acc, cfg, p.A, p.Bt, p.C, p.M, p.N, p.K, group_m, 0, splits, nullptr);
 }
 
-static int do_check(int acc, int cfg, int M, int N, int K) {
+static int do_check(int acc, int cfg, int M, int N, int K, int gm = 0, int splits = 1) {
   Problem p; p.alloc(M, N, K);
   const bool use_naive = double(M) * N * K <= 2.2e10;
   if (use_naive) {
@@ -120,7 +128,8 @@ static int do_check(int acc, int cfg, int M, int N, int K) {
   CK(cudaDeviceSynchronize());
   p.reset_c();
   CK(cudaDeviceSynchronize());
-  int st = run_ours(acc, cfg, p);
+  int st = run_ours(acc, cfg, p, gm, splits);
+  if (splits > 1 && st == 0) st = run_ours(acc, cfg, p, gm, splits);   // twice: the counters must reset themselves
   cudaError_t e = cudaDeviceSynchronize();
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
   if (st != 0 || e != cudaSuccess) {
@@ -137,8 +146,8 @@ static int do_check(int acc, int cfg, int M, int N, int K) {
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost));
   const bool ok = h[0] == 0 && h[2] == 0;
-  printf("CHECK acc=%d cfg=%d(%d) %dx%dx%d  %s mismatches=%llu first=(%lld,%lld) guard_bad=%llu checker=%s\n", acc, cfg,
-         sel, M, N, K, ok ? "PASS" : "FAIL", h[0], h[0] ? (long long)(h[1] / N) : -1LL,
+  printf("CHECK acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  %s mismatches=%llu first=(%lld,%lld) guard_bad=%llu checker=%s\n", acc, cfg,
+         sel, gm, splits, M, N, K, ok ? "PASS" : "FAIL", h[0], h[0] ? (long long)(h[1] / N) : -1LL,
          h[0] ? (long long)(h[1] % N) : -1LL, h[2], use_naive ? "naive" : "cublas");
   if (!ok && h[0]) {
     // dump a small corner of both matrices around the first mismatch to make layout bugs readable
@@ -174,6 +183,27 @@ static float time_ms(F&& f, int iters, int warm = 5) {
   CK(cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a); cudaEventDestroy(b);
   return ms / iters;
+}
+
+// One launch at a time, device time between two events, median over `iters` — what a caller that
+// synchronises after every call (the harness) can at best observe as kernel time.
+template <class F>
+static float time_isolated_ms(F&& f, int iters, int warm = 2) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  std::vector<float> t;
+  for (int i = 0; i < warm + iters; ++i) {
+    CK(cudaEventRecord(a));
+    f();
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    if (i >= warm) t.push_back(ms);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  std::sort(t.begin(), t.end());
+  return t[t.size() / 2];
 }
 
 static void alloc_random(Problem& p, int M, int N, int K) {
@@ -225,17 +255,142 @@ static int do_sweep(int acc, int M, int N, int K, int iters) {
   return 0;
 }
 
+// grid: time every configuration on every shape of the harness grid (+ the extra LLM shape); one CSV line per
+// shape:  M,N,K,cublas_us,best_cfg,best_gm,best_us,<cfg>:<gm>:<us>...   Used by tools/tune_b200.py.
+static int do_grid(int acc, int part, int nparts, double budget_ms) {
+  const int G[10] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384};
+  std::vector<std::array<int, 3>> shapes;
+  for (int a : G) for (int b : G) for (int c : G) shapes.push_back({a, b, c});
+  shapes.push_back({2048, 11008, 4096});
+  const int ncfg = b200_hgemm_num_configs();
+  // one allocation, sized for the largest problem, reused by every shape
+  const size_t maxe = size_t(16384) * 16384;
+  Problem p;
+  CK(cudaMalloc(&p.A, maxe * 2)); CK(cudaMalloc(&p.Bt, maxe * 2));
+  CK(cudaMalloc(&p.Cbuf, maxe * 2)); CK(cudaMalloc(&p.Cref, maxe * 2));
+  p.C = p.Cbuf;
+  fill_normalish<<<g1(maxe), 256>>>(p.A, maxe, 0x1234567u);
+  fill_normalish<<<g1(maxe), 256>>>(p.Bt, maxe, 0x89abcdeu);
+  CK(cudaDeviceSynchronize());
+  for (size_t si = 0; si < shapes.size(); ++si) {
+    if (int(si % nparts) != part) continue;
+    p.M = shapes[si][0]; p.N = shapes[si][1]; p.K = shapes[si][2];
+    const double flops = 2.0 * p.M * p.N * p.K;
+    const double est_ms = flops / 1.0e15 * 1e3 + 0.004;
+    const int iters = std::max(3, std::min(40, int(budget_ms / est_ms)));
+    float blas = time_isolated_ms([&] { cublas_tn(p, p.Cref); }, iters, 2);
+    std::string line;
+    int best_c = -1, best_g = 0, best_s = 1; float best_t = 1e30f;
+    for (int c = 0; c < ncfg; ++c) {
+      int bn, st_, cg; b200_hgemm_config_info(c, &bn, &st_, &cg);
+      if (cg == 2 && p.M <= 128) continue;
+      const int nm = (p.M + 128 * cg - 1) / (128 * cg);
+      const int nn = (p.N + bn - 1) / bn;
+      std::vector<std::pair<int, int>> cands = {{0, 1}};   // (group_m, splits)
+      if (nm * nn > 148 / cg && nm > 1 && nn > 1) {
+        cands = {{1, 1}, {4, 1}, {8, 1}, {16, 1}};
+        if (nm >= 32) cands.push_back({32, 1});
+      }
+      const int nkb = (p.K + 63) / 64;
+      if (cg == 1 && nm * nn * 2 <= 148 && nkb >= 4)
+        for (int sp : {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64})
+          if (sp <= 148 / (nm * nn) && sp <= nkb) cands.push_back({0, sp});
+      for (const auto& cand_ : cands) {
+        const int gm = cand_.first, sp = cand_.second;
+        if (gm > 1 && gm / 2 >= nm) continue;
+        if (run_ours(acc, c, p, gm, sp) != 0 || cudaDeviceSynchronize() != cudaSuccess) { printf("GRIDFAIL %d %d %d cfg %d gm %d sp %d\n", p.M, p.N, p.K, c, gm, sp); return 1; }
+        float t = time_isolated_ms([&] { run_ours(acc, c, p, gm, sp); }, iters, 2);
+        char buf[64]; snprintf(buf, sizeof buf, ",%d:%d:%d:%.2f", c, gm, sp, t * 1e3); line += buf;
+        if (t < best_t) { best_t = t; best_c = c; best_g = gm; best_s = sp; }
+      }
+    }
+    printf("GRID,%d,%d,%d,%d,%.2f,%d,%d,%d,%.2f%s\n", acc, p.M, p.N, p.K, blas * 1e3, best_c, best_g, best_s, best_t * 1e3, line.c_str());
+    fflush(stdout);
+  }
+  return 0;
+}
+
+
+// wall: the harness metric in C++ — host wall clock around ONE call bracketed by device synchronisation
+// (reference benchmarking_utils.py:23-31), mean of per-sample TFLOP/s, our dispatcher against the six library
+// baselines (cuBLASLt auto-tuning runs the reference's 50 + 100 round search first unless rounds are given).
+static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, int tune_bench) {
+  Problem p; alloc_random(p, M, N, K);
+  __half* Brow;   // row-major B [K,N] for the NN baselines
+  CK(cudaMalloc(&Brow, size_t(K) * N * 2));
+  fill_normalish<<<g1(size_t(K) * N), 256>>>(Brow, size_t(K) * N, 0x5555u);
+  CK(cudaDeviceSynchronize());
+  if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
+  int cand[2] = {0, 0}; float best_ms[2] = {0, 0};
+  for (int lay = 0; lay < 2; ++lay) {
+    int st = b200_bl_lt_autotune_find(acc, lay, M, N, K, tune_warm, tune_bench);
+    if (st) { printf("autotune find failed %d\n", st); return 1; }
+    b200_bl_lt_autotune_info(acc, lay, &cand[lay], &best_ms[lay]);
+  }
+  struct Fn { const char* name; std::function<int()> f; };
+  std::vector<Fn> fns = {
+      {"ours", [&] { return run_ours(acc, -1, p); }},
+      {"cublas_tn", [&] { return b200_bl_cublas(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
+      {"cublas_nn", [&] { return b200_bl_cublas(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
+      {"lt_heur_tn", [&] { return b200_bl_lt_heuristic(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
+      {"lt_heur_nn", [&] { return b200_bl_lt_heuristic(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
+      {"lt_auto_tn", [&] { return b200_bl_lt_autotune(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
+      {"lt_auto_nn", [&] { return b200_bl_lt_autotune(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
+  };
+  const double flops = 2.0 * M * N * K;
+  std::vector<double> sum_tf(fns.size(), 0.0), sum_ms(fns.size(), 0.0);
+  std::vector<int> order(fns.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
+  std::mt19937 rng(12345);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  for (auto& fn : fns) { if (fn.f()) { printf("warm-up call failed: %s\n", fn.name); return 1; } }
+  CK(cudaDeviceSynchronize());
+  int samples = 0;
+  const auto t_end = now() + std::chrono::duration<double>(seconds);
+  const auto t_warm = now() + std::chrono::duration<double>(seconds * 0.25);
+  bool warm = true;
+  while (true) {
+    if (warm && now() > t_warm) { warm = false; }
+    if (!warm && now() > t_end + std::chrono::duration<double>(seconds * 0.25)) break;
+    std::shuffle(order.begin(), order.end(), rng);
+    for (int id : order) {
+      CK(cudaDeviceSynchronize());
+      const auto t0 = now();
+      fns[id].f();
+      CK(cudaDeviceSynchronize());
+      const double ms = std::chrono::duration<double, std::milli>(now() - t0).count();
+      if (!warm) { sum_tf[id] += flops / ms * 1e-9; sum_ms[id] += ms; }
+    }
+    if (!warm) ++samples;
+  }
+  int cfg, gm, sp; b200_hgemm_select(acc, M, N, K, &cfg, &gm, &sp);
+  printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0]);
+  for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.3f", fns[i].name, sum_tf[i] / samples);
+  const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
+  printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3);
+  fflush(stdout);
+  cudaFree(Brow);
+  p.release();
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: see source header\n"); return 64; }
   CK(cudaSetDevice(0));
   cublasCreate(&g_blas);
   std::string mode = argv[1];
   if (mode == "check" && argc >= 7)
-    return do_check(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]));
+    return do_check(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 0,
+                    argc > 8 ? atoi(argv[8]) : 1);
   if (mode == "time" && argc >= 7)
     return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20);
   if (mode == "sweep" && argc >= 6)
     return do_sweep(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 20);
+  if (mode == "wall" && argc >= 6)
+    return do_wall(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atof(argv[6]) : 1.0,
+                   argc > 7 ? atoi(argv[7]) : 0, argc > 8 ? atoi(argv[8]) : 0);
+  if (mode == "grid" && argc >= 3)
+    return do_grid(atoi(argv[2]), argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atof(argv[5]) : 3.0);
   printf("bad arguments\n");
   return 64;
 }

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 
 #include "hgemm_sm100.cuh"
 
@@ -132,10 +133,51 @@ inline int validate(const void* A, const void* Bt, const void* C, int M, int N, 
   return kOk;
 }
 
-// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs".
+// Split-K scratch: fp32 partial tiles + arrival counters, allocated on first use (one per device and
+// stream; a handful of streams at most) and kept for the life of the process. Counters are zero between
+// launches (the kernel resets them), so consecutive launches on a stream need no host-side clearing.
+struct SplitKScratch {
+  int dev = -1; cudaStream_t stream = nullptr; float* ws = nullptr; unsigned* ctr = nullptr;
+};
+constexpr size_t kSplitKWsBytes = size_t(160) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
+inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
+  static thread_local SplitKScratch pool[8];
+  SplitKScratch* free_slot = nullptr;
+  for (auto& e : pool) {
+    if (e.ws && e.dev == dev && e.stream == stream) { *out = &e; return kOk; }
+    if (!e.ws && !free_slot) free_slot = &e;
+  }
+  if (!free_slot) return kBadConfig;
+  cudaError_t err = cudaMalloc(&free_slot->ws, kSplitKWsBytes);
+  if (err != cudaSuccess) return int(err);
+  err = cudaMalloc(&free_slot->ctr, 2 * kMaxSplitTiles * sizeof(unsigned));
+  if (err != cudaSuccess) { cudaFree(free_slot->ws); free_slot->ws = nullptr; return int(err); }
+  err = cudaMemsetAsync(free_slot->ctr, 0, 2 * kMaxSplitTiles * sizeof(unsigned), stream);
+  if (err != cudaSuccess) return int(err);
+  free_slot->dev = dev; free_slot->stream = stream;
+  *out = free_slot;
+  return kOk;
+}
+
+// Largest usable split factor for this problem/config: units must fit the SMs (one CTA per unit), every
+// split must own at least one k-block, and the partial tiles must fit the workspace.
+template <class Cfg>
+int clamp_splits(int splits, int M, int N, int K, int num_sms) {
+  if (splits <= 1 || Cfg::CTA_GROUP != 1) return 1;
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);
+  const int nkb = (K + kBlockK - 1) / kBlockK;
+  if (tiles > kMaxSplitTiles) return 1;
+  splits = std::min(splits, std::min(num_sms / tiles, std::min(nkb, kBlockM)));
+  while (splits > 1 && (splits - 1) * ((nkb + splits - 1) / splits) >= nkb) --splits;   // no empty split
+  while (splits > 1 && size_t(tiles) * splits * kBlockM * Cfg::BN * sizeof(float) > kSplitKWsBytes) --splits;
+  return std::max(splits, 1);
+}
+
+// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". splits > 1 requests
+// split-K (clamped to what the problem allows; only for CTA_GROUP == 1 configurations).
 template <class Cfg>
 int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStream_t stream,
-           int group_m = 0, int max_ctas = 0) {
+           int group_m = 0, int max_ctas = 0, int splits = 1) {
   int st = validate(A, Bt, C, M, N, K);
   if (st != kOk) return st;
   const DeviceInfo& di = device_info();
@@ -160,7 +202,17 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   const int num_tiles = num_m_blocks * num_n_blocks;
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CTA_GROUP;
   if (workers < 1) workers = 1;
-  if (workers > num_tiles) workers = num_tiles;
+  splits = clamp_splits<Cfg>(splits, M, N, K, workers);
+  float* ws = nullptr;
+  unsigned* ctr = nullptr;
+  if (splits > 1) {
+    SplitKScratch* sk = nullptr;
+    if ((st = splitk_scratch(di.dev, stream, &sk)) != kOk) return st;
+    ws = sk->ws; ctr = sk->ctr;
+    workers = num_tiles * splits;          // exactly one CTA per (tile, split) unit
+  } else if (workers > num_tiles) {
+    workers = num_tiles;
+  }
   if (group_m <= 0) group_m = (Cfg::CTA_GROUP == 2) ? 8 : 16;
 
   cudaLaunchConfig_t cfg{};
@@ -175,7 +227,8 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (Cfg::CTA_GROUP > 1) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, ws, ctr,
+                                     static_cast<__half*>(C));
   return e == cudaSuccess ? kOk : int(e);
 }
 

@@ -94,12 +94,108 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m_blocks, int num
   return c;
 }
 
+
+constexpr int kMaxSplitTiles = 256;   // split-K is only used when tiles * splits <= #SMs
+
+// Split-K epilogue (CTA_GROUP == 1, one (tile, split) unit per CTA, all units resident at once).
+//   phase 1  every split writes its 128 x BN fp32 partial tile to the workspace slot (tile, split);
+//   barrier  a per-tile arrival counter in global memory (release/acquire at gpu scope);
+//   phase 2  split s sums a contiguous 1/splits slice of the tile's rows over ALL partials in the fixed
+//            order s' = 0..splits-1 (deterministic), rounds once to fp16 and stores to C.
+// The last split to finish phase 2 zeroes both counters, so the next launch on the stream starts clean.
+template <class Cfg>
+__device__ __forceinline__ void splitk_epilogue(uint32_t taddr0, int q, int lane, int tile, int split, int splits,
+                                                int m_base, int n0, int M, int N, float* __restrict__ ws,
+                                                unsigned* __restrict__ ctr, __half* __restrict__ C) {
+  using namespace ptx;
+  constexpr int BN = Cfg::BN;
+  const int row = q * 32 + lane;
+  float* slot = ws + (size_t(tile) * splits + split) * (kBlockM * BN) + size_t(row) * BN;
+#pragma unroll
+  for (int j = 0; j < BN / 32; ++j) {
+    float f[32];
+    if constexpr (Cfg::ACC_F32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr0 + j * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    } else {
+      // fp16 accumulators: 32 columns arrive packed two per register in the first 16 registers
+      uint32_t v[32];
+      tmem_ld_32x32b_x32_pack16(taddr0 + (j / 2) * 64, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&v[(j & 1) * 16 + i]);
+        f[2 * i] = __low2float(h);
+        f[2 * i + 1] = __high2float(h);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      __stcg(reinterpret_cast<float4*>(slot + j * 32) + i, make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
+  }
+  // publish the partial, then wait until every split of this tile has published its own
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int e = q * 32 + lane;   // 0..127 over the four epilogue warps
+  if (e == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + tile) : "memory");
+    unsigned seen = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr + tile) : "memory");
+      if (seen < unsigned(splits)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { printf("b200_hgemm watchdog: split-K tile %d saw %u/%d arrivals\n", tile, seen, splits); __trap(); }
+      }
+    } while (seen < unsigned(splits));
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // phase 2: rows [r0, r1) of the tile belong to this split
+  const int rows_per = (kBlockM + splits - 1) / splits;
+  const int r0 = split * rows_per;
+  const int r1 = min(kBlockM, r0 + rows_per);
+  constexpr int V = BN / 4;      // float4 per row
+  const float* tile_ws = ws + size_t(tile) * splits * (kBlockM * BN);
+  for (int i = e; i < (r1 - r0) * V; i += 128) {
+    const int r = r0 + i / V, c4 = i % V;
+    const int gm = m_base + r, gn = n0 + c4 * 4;
+    if (gm >= M || gn >= N) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(tile_ws + size_t(r) * BN) + c4;
+#pragma unroll 4
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 p = __ldcg(src + size_t(sp) * (kBlockM * BN / 4));
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    uint2 out;
+    out.x = pack_f16x2_rn(acc.x, acc.y);
+    out.y = pack_f16x2_rn(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (e == 0) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr + kMaxSplitTiles + tile) : "memory");
+    if (old == unsigned(splits - 1)) {   // everyone is past the arrival wait: safe to reset for the next launch
+      ctr[tile] = 0;
+      ctr[kMaxSplitTiles + tile] = 0;
+      __threadfence();
+    }
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kNumThreads, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, 128}
                 const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, LOAD_N}
                 const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {64, 32}
-                int M, int N, int K, int group_m) {
+                int M, int N, int K, int group_m,
+                int splits,                       // split-K factor; > 1 only with CTA_GROUP == 1, one unit per CTA
+                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (splits > 1)
+                unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
+                __half* __restrict__ c_raw        /* C base pointer, used by the split-K reduction's direct stores */) {
   constexpr int BN = Cfg::BN;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CG = Cfg::CTA_GROUP;
@@ -129,6 +225,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
   const int num_workers = gridDim.x / CG;       // CTAs (CG=1) or CTA pairs (CG=2)
   const int worker = blockIdx.x / CG;
+  // A work unit is (tile, k-split). splits == 1: units == tiles, walked persistently. splits > 1: the host
+  // launches exactly one CTA per unit (units <= SMs), so the sibling splits of a tile are all resident.
+  const int num_units = num_tiles * splits;
+  const int kb_per_split = (num_k_blocks + splits - 1) / splits;
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && elect_one()) {
@@ -165,11 +265,14 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       int stage = 0; uint32_t phase = 0;
       // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
       const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
-      for (int t = worker; t < num_tiles; t += num_workers) {
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int t = u / splits;
+        const int kb0 = (u - t * splits) * kb_per_split;
+        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
         const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
         const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM;
         const int n0 = tc.n_blk * BN + int(cta_rank) * Cfg::LOAD_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
           const uint32_t fb = full0 + 8 * stage;
@@ -185,11 +288,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = worker; t < num_tiles; t += num_workers) {
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int kb0 = (u % splits) * kb_per_split;
+        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
         mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
           const uint64_t da = make_smem_desc(smem_a + stage * Cfg::A_STAGE_BYTES);
@@ -197,7 +302,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // +32 B per K step inside the 128 B swizzle row == +2 in the (addr >> 4) field
-            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
           }
           // free the smem slot (in both CTAs of a pair) once these MMAs have read it
           if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
@@ -218,13 +323,21 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const uint32_t sw = uint32_t(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
     int buf = 0;
-    for (int t = worker; t < num_tiles; t += num_workers) {
+    for (int u = worker; u < num_units; u += num_workers) {
+      const int t = u / splits;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
       const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM + q * 32;
       const int n0 = tc.n_blk * BN;
       mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
+      if constexpr (CG == 1) {
+        if (splits > 1) {
+          splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, tc.m_blk * kBlockM, n0, M, N,
+                               splitk_ws, splitk_ctr, c_raw);
+          continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
+        }
+      }
 #pragma unroll
       for (int j = 0; j < BN / kEpiChunkN; ++j) {
         uint32_t packed[32];

@@ -46,11 +46,14 @@ int b200_hgemm_num_configs(void);
 int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group);
 /* The configuration the dispatcher uses for this problem (acc_bits = 32 or 16). */
 int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
-/* Same, also reporting the rasterisation group (0 = kernel default). Returns 0 or a negative status. */
-int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m);
-/* Run one explicit configuration. group_m <= 0 and max_ctas <= 0 select the defaults. */
+/* Same, also reporting the rasterisation group (0 = kernel default) and the split-K factor (1 = none).
+ * Returns 0 or a negative status. */
+int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m, int* splits);
+/* Run one explicit configuration. group_m <= 0 and max_ctas <= 0 select the defaults; splits > 1 asks for
+ * split-K (cta_group 1 configurations only; clamped so that tiles x splits fits the SMs). The split-K
+ * reduction is deterministic (fixed summation order) and uses a lazily allocated per-stream workspace. */
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C,
-                          int M, int N, int K, int group_m, int max_ctas, void* stream);
+                          int M, int N, int K, int group_m, int max_ctas, int splits, void* stream);
 
 /* End-to-end form with HOST buffers (pageable or pinned): copies A and B_kmajor to the device,
  * runs the GEMM and copies C back, synchronising before it returns. This is the call bench.py

@@ -37,8 +37,8 @@ def test_config_table_and_dispatch(built_libs):
     for acc in ("fp32", "fp16"):
         for mnk in ((64, 4096, 64), (4096, 4096, 4096), (8192, 8192, 8192), (2048, 11008, 4096), (64, 64, 64),
                     (16384, 16384, 16384), (200, 328, 72)):
-            cid, gm = capi.select(acc, *mnk)
-            assert cid in ids and gm >= 0
+            cid, gm, sp = capi.select(acc, *mnk)
+            assert cid in ids and gm >= 0 and sp >= 1
             if mnk[0] <= 128:
                 assert cfgs[cid]["cta_group"] == 1     # a CTA pair would waste its second half on padding
 
@@ -53,8 +53,8 @@ def test_argument_validation_happens_before_any_cuda_call(built_libs):
     assert lib.b200_hgemm_f16acc(p, None, p, p, 64, 64, 60, None) == -2                 # K % 8 != 0
     assert lib.b200_hgemm_f16acc(p, None, p, p, 64, 60, 64, None) == -2                 # N % 8 != 0
     assert lib.b200_hgemm_f32acc(p + 2, None, p, p, 64, 64, 64, None) == -2             # misaligned A
-    assert lib.b200_hgemm_run_config(32, 99, p, p, p, 64, 64, 64, 0, 0, None) == -6     # unknown config
-    assert lib.b200_hgemm_run_config(8, 0, p, p, p, 64, 64, 64, 0, 0, None) == -6       # unknown accumulator
+    assert lib.b200_hgemm_run_config(32, 99, p, p, p, 64, 64, 64, 0, 0, 1, None) == -6     # unknown config
+    assert lib.b200_hgemm_run_config(8, 0, p, p, p, 64, 64, 64, 0, 0, 1, None) == -6       # unknown accumulator
     assert "16-byte" in capi.strerror(-2)
     assert capi.launch_count() == 0
 
