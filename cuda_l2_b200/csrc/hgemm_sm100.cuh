@@ -231,12 +231,35 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const int kb_per_split = (num_k_blocks + splits - 1) / splits;
 
   // ------------------------------------------------------------------ one-time setup
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    tma_prefetch_desc(&tmap_c);
-  }
-  if (warp == 1 && elect_one()) {
+  // Warp 0's elected thread owns the mbarriers and is the TMA producer. Its state lives in registers across
+  // the setup barrier so that (single-CTA groups only) the first ring of loads is already in flight while
+  // TMEM is being allocated and the other warps are still arriving.
+  const bool is_producer = (warp == 0) && elect_one();
+  int p_unit = worker, p_kb = 0, p_stage = 0;
+  uint32_t p_phase = 0;
+  // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
+  const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
+  auto produce = [&](int budget) {
+    while (p_unit < num_units && budget > 0) {
+      const int t = p_unit / splits;
+      const int kb0 = (p_unit - t * splits) * kb_per_split;
+      const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
+      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
+      const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM;
+      const int n0 = tc.n_blk * BN + int(cta_rank) * Cfg::LOAD_N;
+      for (; kb0 + p_kb < kb1 && budget > 0; ++p_kb, --budget) {
+        const int kb = kb0 + p_kb;
+        mbar_wait(bar_empty + 8 * p_stage, p_phase ^ 1);
+        if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * p_stage, Cfg::STAGE_BYTES * CG);
+        const uint32_t fb = full0 + 8 * p_stage;
+        tma_load_2d<CG>(smem_a + p_stage * Cfg::A_STAGE_BYTES, &tmap_a, fb, kb * kBlockK, m0);
+        tma_load_2d<CG>(smem_b + p_stage * Cfg::B_STAGE_BYTES, &tmap_b, fb, kb * kBlockK, n0);
+        if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
+      }
+      if (kb0 + p_kb >= kb1) { p_kb = 0; p_unit += num_workers; }
+    }
+  };
+  if (is_producer) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);    // producer's arrive.expect_tx (leader CTA's only, for a pair)
       mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
@@ -246,6 +269,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_tmem_empty + 8 * a, 4 * CG);  // one arrive per epilogue warp of every CTA in the group
     }
     fence_mbar_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if constexpr (CG == 1) produce(STAGES);   // all barriers these loads touch are this CTA's own, just initialised
+    tma_prefetch_desc(&tmap_c);
   }
   if (warp == 2) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
@@ -261,27 +288,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
     // ===== TMA producer (one thread) =====
-    if (elect_one()) {
-      int stage = 0; uint32_t phase = 0;
-      // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
-      const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
-      for (int u = worker; u < num_units; u += num_workers) {
-        const int t = u / splits;
-        const int kb0 = (u - t * splits) * kb_per_split;
-        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
-        const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-        const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM;
-        const int n0 = tc.n_blk * BN + int(cta_rank) * Cfg::LOAD_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
-          const uint32_t fb = full0 + 8 * stage;
-          tma_load_2d<CG>(smem_a + stage * Cfg::A_STAGE_BYTES, &tmap_a, fb, kb * kBlockK, m0);
-          tma_load_2d<CG>(smem_b + stage * Cfg::B_STAGE_BYTES, &tmap_b, fb, kb * kBlockK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
+    if (is_producer) produce(0x7fffffff);
   } else if (warp == 1) {
     // ===== MMA issuer (one thread of the leader CTA) =====
     if (is_leader && elect_one()) {
@@ -384,7 +391,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait_all();
+    // smem may be released once the bulk stores have READ it; their global writes complete with the grid
+    if (lane == 0) tma_store_wait_read<0>();
   }
 
   // ------------------------------------------------------------------ teardown

@@ -1,0 +1,169 @@
+"""Farm the (M,N,K) sweep over the GPUs of one box — one problem per GPU at a time, no collective on the GEMM path.
+
+The reference evaluates one shape per invocation of eval_one_file.sh and has no multi-GPU notion beyond
+``--gpu_device_id`` (benchmarking_offline.py:27,53). Every shape is an independent unit, so the sweep
+shards trivially: shapes are sorted longest-first by an analytic cost and dealt round-robin to ranks (LPT order),
+each rank pins one GPU and evaluates its share, results are gathered on rank 0 (``all_gather_object`` over
+gloo/nccl when launched under torchrun, or through per-rank JSONL files when the orchestrator spawns workers itself).
+
+Engines:
+  wall     ``dev_check wall``: the harness metric (wall clock around one call + device sync, mean TFLOP/s) in C++,
+           our dispatcher vs cuBLAS / cuBLASLt-heuristic / cuBLASLt-auto-tuning, both layouts. Seconds per shape.
+  harness  the reference-style ``eval_one_file.sh`` (JIT build + 1 correctness + 7 benchmark processes). Minutes per shape.
+"""
+from __future__ import annotations
+
+import csv
+import itertools
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+GRID = (64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384)
+EXTRA_SHAPES = ((2048, 11008, 4096),)
+CSV_COLUMNS = ["mnk", "torch.matmul", "cuBLAS-tn", "cuBLAS-nn", "cuBLAS-max", "cuBLASLt-heuristic-tn",
+               "cuBLASLt-heuristic-nn", "cuBLASLt-heuristic-max", "cuBLASLt-auto-tuning-tn", "cuBLASLt-auto-tuning-nn",
+               "cuBLASLt-auto-tuning-max"]     # header of the reference's eval_results/*.csv
+
+
+def grid_shapes() -> list[tuple[int, int, int]]:
+    return list(itertools.product(GRID, GRID, GRID)) + list(EXTRA_SHAPES)
+
+
+def estimated_cost(shape, tflops: float = 1400.0, gbs: float = 6000.0, fixed_s: float = 2.5) -> float:
+    """Seconds a worker spends on a shape: fixed per-shape overhead (tuning, process start) + ~3000 GEMMs."""
+    m, n, k = shape
+    t = max(2.0 * m * n * k / (tflops * 1e12), 2.0 * (m * k + n * k + m * n) / (gbs * 1e9), 4e-6)
+    return fixed_s + 3000 * t
+
+
+def partition(shapes, world: int) -> list[list[tuple[int, int, int]]]:
+    """Longest-processing-time-first onto the least loaded rank: deterministic, every shape exactly once."""
+    loads = [0.0] * world
+    parts: list[list] = [[] for _ in range(world)]
+    for s in sorted(shapes, key=lambda s: (-estimated_cost(s), s)):
+        r = min(range(world), key=lambda i: (loads[i], i))
+        parts[r].append(s)
+        loads[r] += estimated_cost(s)
+    return parts
+
+
+def speedup_row(mnk: str, tf: dict) -> dict:
+    """One row of the reference's CSV schema from absolute TFLOP/s (ours + baselines); "-max" is the harder
+    of the two layouts, i.e. the smaller speed-up (summarize_result.py:43-53)."""
+    ours = tf["ours"]
+    row = {"mnk": mnk, "torch.matmul": (ours / tf["matmul"]) if tf.get("matmul") else ""}
+    for fam, key in (("cuBLAS", "cublas"), ("cuBLASLt-heuristic", "lt_heur"), ("cuBLASLt-auto-tuning", "lt_auto")):
+        tn, nn = ours / tf[f"{key}_tn"], ours / tf[f"{key}_nn"]
+        row[f"{fam}-tn"], row[f"{fam}-nn"], row[f"{fam}-max"] = tn, nn, min(tn, nn)
+    return row
+
+
+def parse_wall_line(line: str) -> dict:
+    f = line.strip().split(",")
+    assert f[0] == "WALL"
+    out = {"acc": int(f[1]), "m": int(f[2]), "n": int(f[3]), "k": int(f[4])}
+    for tok in f[5:]:
+        key, val = tok.split("=")
+        try:
+            out[key] = float(val)
+        except ValueError:
+            out[key] = val
+    return out
+
+
+def run_wall_engine(shape, acc_bits: int, seconds: float, tune_rounds: tuple[int, int], gpu: int | None) -> dict:
+    exe = REPO / "cuda_l2_b200" / "lib" / "dev_check"
+    if not exe.exists():
+        raise RuntimeError(f"{exe} missing: run __graft_entry__.build() first (no fallback)")
+    env = dict(os.environ)
+    if gpu is not None:
+        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    m, n, k = shape
+    cmd = [str(exe), "wall", str(acc_bits), str(m), str(n), str(k), str(seconds), str(tune_rounds[0]), str(tune_rounds[1])]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for line in r.stdout.splitlines():
+        if line.startswith("WALL,"):
+            return parse_wall_line(line)
+    raise RuntimeError(f"dev_check wall failed for {shape}: rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+
+
+def run_partition(rank: int, shapes, engine, out_path: Path | None = None, done: set | None = None) -> list[dict]:
+    """Evaluate this rank's share with ``engine(shape) -> dict``; append each result to ``out_path`` (JSONL) so an
+    interrupted sweep resumes where it stopped. A failing shape is recorded, not fatal (per-shape isolation)."""
+    results = []
+    for s in shapes:
+        key = "_".join(map(str, s))
+        if done and key in done:
+            continue
+        try:
+            rec = dict(engine(s), mnk=key, rank=rank, ok=True)
+        except Exception as e:  # keep the sweep alive; the failure list is part of the report
+            rec = {"mnk": key, "rank": rank, "ok": False, "error": str(e)[:500]}
+        results.append(rec)
+        if out_path is not None:
+            with open(out_path, "a") as f:
+                f.write(json.dumps(rec) + "\n")
+    return results
+
+
+def load_done(paths) -> dict[str, dict]:
+    done = {}
+    for p in paths:
+        if Path(p).exists():
+            for line in Path(p).read_text().splitlines():
+                try:
+                    rec = json.loads(line)
+                except json.JSONDecodeError:
+                    continue
+                if rec.get("ok"):
+                    done[rec["mnk"]] = rec
+    return done
+
+
+def gather(results: list[dict]) -> list[list[dict]] | None:
+    """All ranks' result lists on rank 0 (None elsewhere); a plain list when not running under torch.distributed."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [results]
+    bucket = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(results, bucket, dst=0)
+    return bucket
+
+
+def write_reports(records: list[dict], out_csv: Path, peak_tflops: float, peak_gbs: float) -> dict:
+    """The reference-schema speed-up CSV plus an extended CSV with absolute TFLOP/s and roofline fractions."""
+    ok = sorted((r for r in records if r.get("ok")), key=lambda r: tuple(int(x) for x in r["mnk"].split("_")))
+    out_csv.parent.mkdir(parents=True, exist_ok=True)
+    with open(out_csv, "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=CSV_COLUMNS)
+        w.writeheader()
+        for r in ok:
+            w.writerow(speedup_row(r["mnk"], r))
+    ext = out_csv.with_name(out_csv.stem + "_absolute.csv")
+    cols = ["mnk", "ours", "cublas_tn", "cublas_nn", "lt_heur_tn", "lt_heur_nn", "lt_auto_tn", "lt_auto_nn",
+            "speedup_vs_lt_auto_max", "roofline_bound", "roofline_frac", "cfg", "gm", "splits"]
+    wins = 0
+    with open(ext, "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=cols)
+        w.writeheader()
+        for r in ok:
+            m, n, k = (int(x) for x in r["mnk"].split("_"))
+            flops, byts = 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n)
+            t_tensor, t_hbm = flops / (peak_tflops * 1e12), byts / (peak_gbs * 1e9)
+            t_ours = flops / (r["ours"] * 1e12)
+            row = {c: r.get(c, "") for c in cols}
+            row["roofline_bound"] = "tensor" if t_tensor >= t_hbm else "hbm"
+            row["roofline_frac"] = max(t_tensor, t_hbm) / t_ours
+            w.writerow(row)
+            wins += r["speedup_vs_lt_auto_max"] >= 1.0
+    n = len(ok)
+    mean = sum(r["speedup_vs_lt_auto_max"] for r in ok) / n if n else float("nan")
+    return {"shapes": n, "failed": [r["mnk"] for r in records if not r.get("ok")],
+            "won_vs_lt_auto_max": wins, "win_fraction": wins / n if n else float("nan"), "mean_speedup_vs_lt_auto_max": mean,
+            "aggregate_tflops": sum(2.0 * eval(r["mnk"].replace("_", "*")) for r in ok) /
+                                sum(2.0 * eval(r["mnk"].replace("_", "*")) / (r["ours"] * 1e12) for r in ok) * 1e-12 if n else 0.0}

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Run the (M,N,K) sweep across the GPUs of one box (BASELINE config 5) and write the eval_results CSVs.
+
+    python farm_sweep.py --gpus 8 --acc_precise fp32 --seconds 0.5                     # spawns one worker per GPU
+    python -m torch.distributed.run --nproc-per-node 8 farm_sweep.py --acc_precise fp32  # same, under torchrun
+    python farm_sweep.py --gpus 1 --shapes 64_4096_64,4096_4096_4096 --seconds 1         # a few shapes
+
+One problem per GPU at a time, no NCCL on the GEMM path; results are gathered at the end. Interrupted runs resume
+from {base_dir}/worker_*.jsonl. Output: eval_results/cuda_l2_b200_<ACC>_speedup_<mode>.csv in the reference's schema
+plus *_absolute.csv (TFLOP/s, roofline fraction) and *_summary.json (win fraction vs cuBLASLt-auto-tuning-max).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+from cuda_l2_b200 import farm  # noqa: E402
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=0, help="GPUs to use (0 = all visible; ignored under torchrun)")
+    p.add_argument("--acc_precise", default="fp32", choices=["fp32", "fp16"])
+    p.add_argument("--seconds", type=float, default=0.5, help="sampling time per shape (wall engine)")
+    p.add_argument("--tune_rounds", default="10,30", help="cuBLASLt auto-tuning warm-up,timed rounds (reference: 50,100)")
+    p.add_argument("--shapes", default="grid", help="'grid' (1000 + 2048_11008_4096) or a comma list of M_N_K")
+    p.add_argument("--limit", type=int, default=0, help="evaluate only the first N shapes of the cost-sorted list")
+    p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
+    p.add_argument("--out_dir", default=str(REPO / "eval_results"))
+    p.add_argument("--mode", default="offline", choices=["offline"])
+    p.add_argument("--worker", type=int, default=-1, help=argparse.SUPPRESS)
+    p.add_argument("--world", type=int, default=0, help=argparse.SUPPRESS)
+    return p.parse_args(argv)
+
+
+def shape_list(args):
+    if args.shapes == "grid":
+        shapes = farm.grid_shapes()
+    else:
+        shapes = [tuple(int(x) for x in s.split("_")) for s in args.shapes.split(",")]
+    if args.limit:
+        shapes = sorted(shapes, key=lambda s: -farm.estimated_cost(s))[: args.limit]
+    return shapes
+
+
+def worker(args, rank, world, gpu):
+    bits = 32 if args.acc_precise == "fp32" else 16
+    warm, bench = (int(x) for x in args.tune_rounds.split(","))
+    mine = farm.partition(shape_list(args), world)[rank]
+    base = Path(args.base_dir)
+    base.mkdir(parents=True, exist_ok=True)
+    out = base / f"worker_{args.acc_precise}_{rank}.jsonl"
+    done = set(farm.load_done([out]))
+    engine = lambda s: farm.run_wall_engine(s, bits, args.seconds, (warm, bench), gpu)
+    return farm.run_partition(rank, mine, engine, out, done)
+
+
+def finish(args, world):
+    import bench
+    base = Path(args.base_dir)
+    recs = list(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))).values())
+    wanted = {"_".join(map(str, s)) for s in shape_list(args)}
+    recs = [r for r in recs if r["mnk"] in wanted]
+    peak_tf, peak_hbm, src = bench.peaks()
+    acc_dir = "F32F16F16F32" if args.acc_precise == "fp32" else "F16F16F16F16"
+    out_csv = Path(args.out_dir) / f"cuda_l2_b200_{acc_dir}_speedup_{args.mode}.csv"
+    summary = farm.write_reports(recs, out_csv, peak_tf, peak_hbm)
+    summary.update({"n_gpus": world, "peak_source": src, "seconds_per_shape": args.seconds, "tune_rounds": args.tune_rounds,
+                    "missing": sorted(wanted - {r["mnk"] for r in recs})[:20]})
+    out_csv.with_name(out_csv.stem + "_summary.json").write_text(json.dumps(summary, indent=1))
+    print(json.dumps(summary))
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    t0 = time.time()
+    if "RANK" in os.environ and args.worker < 0:          # under torchrun: one rank per GPU
+        import torch.distributed as dist
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        dist.init_process_group("gloo")                    # results are tiny Python objects; no GPU collective needed
+        worker(args, rank, world, int(os.environ.get("LOCAL_RANK", rank)))
+        dist.barrier()
+        if rank == 0:
+            finish(args, world)
+        dist.destroy_process_group()
+        return 0
+    if args.worker >= 0:                                   # child of the self-spawning orchestrator
+        worker(args, args.worker, args.world, args.worker)
+        return 0
+    n = args.gpus
+    if n <= 0:
+        import torch
+        n = max(1, torch.cuda.device_count())
+    procs = [subprocess.Popen([sys.executable, __file__, *sys.argv[1:], "--worker", str(i), "--world", str(n)]) for i in range(n)]
+    rc = [p.wait() for p in procs]
+    finish(args, n)
+    print(f"sweep wall time {time.time() - t0:.1f} s on {n} GPU(s); worker exit codes {rc}")
+    return 0 if all(r == 0 for r in rc) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
