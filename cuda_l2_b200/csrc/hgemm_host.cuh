@@ -167,7 +167,7 @@ int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);
   const int nkb = (K + kBlockK - 1) / kBlockK;
   if (tiles > kMaxSplitTiles) return 1;
-  splits = std::min(splits, std::min(num_sms / tiles, std::min(nkb, kBlockM)));
+  splits = std::min(splits, std::min(num_sms / tiles, std::min(nkb, 32)));   // <= 32: the slices of all partials must fit the pipeline smem
   while (splits > 1 && (splits - 1) * ((nkb + splits - 1) / splits) >= nkb) --splits;   // no empty split
   while (splits > 1 && size_t(tiles) * splits * kBlockM * Cfg::BN * sizeof(float) > kSplitKWsBytes) --splits;
   return std::max(splits, 1);

@@ -106,7 +106,8 @@ constexpr int kMaxSplitTiles = 256;   // split-K is only used when tiles * split
 template <class Cfg>
 __device__ __forceinline__ void splitk_epilogue(uint32_t taddr0, int q, int lane, int tile, int split, int splits,
                                                 int m_base, int n0, int M, int N, float* __restrict__ ws,
-                                                unsigned* __restrict__ ctr, __half* __restrict__ C) {
+                                                unsigned* __restrict__ ctr, __half* __restrict__ C,
+                                                uint32_t red_smem, uint32_t red_bar) {
   using namespace ptx;
   constexpr int BN = Cfg::BN;
   const int row = q * 32 + lane;
@@ -152,27 +153,36 @@ __device__ __forceinline__ void splitk_epilogue(uint32_t taddr0, int q, int lane
     } while (seen < unsigned(splits));
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  // phase 2: rows [r0, r1) of the tile belong to this split
+  // phase 2: rows [r0, r1) of the tile belong to this split. Their slices of all `splits` partials are pulled
+  // into the (now idle) pipeline smem with 1-D bulk copies — one contiguous slice per partial — and summed there.
   const int rows_per = (kBlockM + splits - 1) / splits;
   const int r0 = split * rows_per;
   const int r1 = min(kBlockM, r0 + rows_per);
-  constexpr int V = BN / 4;      // float4 per row
-  const float* tile_ws = ws + size_t(tile) * splits * (kBlockM * BN);
-  for (int i = e; i < (r1 - r0) * V; i += 128) {
-    const int r = r0 + i / V, c4 = i % V;
-    const int gm = m_base + r, gn = n0 + c4 * 4;
-    if (gm >= M || gn >= N) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* src = reinterpret_cast<const float4*>(tile_ws + size_t(r) * BN) + c4;
-#pragma unroll 4
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4 p = __ldcg(src + size_t(sp) * (kBlockM * BN / 4));
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  if (r0 < r1) {
+    const uint32_t slice_bytes = uint32_t(r1 - r0) * BN * 4u;
+    const float* tile_ws = ws + size_t(tile) * splits * (kBlockM * BN) + size_t(r0) * BN;
+    if (e == 0) {
+      fence_proxy_async_all();   // the partials were written through the generic proxy by other CTAs
+      mbar_arrive_expect_tx(red_bar, slice_bytes * uint32_t(splits));
+      for (int sp = 0; sp < splits; ++sp)
+        bulk_load_1d(red_smem + uint32_t(sp) * slice_bytes, tile_ws + size_t(sp) * (kBlockM * BN), slice_bytes, red_bar);
     }
-    uint2 out;
-    out.x = pack_f16x2_rn(acc.x, acc.y);
-    out.y = pack_f16x2_rn(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
+    mbar_wait(red_bar, 0);
+    constexpr int V = BN / 4;      // float4 per row
+    for (int i = e; i < (r1 - r0) * V; i += 128) {
+      const int r = r0 + i / V, c4 = i % V;
+      const int gm = m_base + r, gn = n0 + c4 * 4;
+      if (gm >= M || gn >= N) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < splits; ++sp) {   // fixed order: deterministic
+        const float4 p = ld_shared_v4f(red_smem + uint32_t(sp) * slice_bytes + uint32_t(i) * 16u);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      uint2 out;
+      out.x = pack_f16x2_rn(acc.x, acc.y);
+      out.y = pack_f16x2_rn(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
+    }
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (e == 0) {
@@ -211,8 +221,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const uint32_t bar_empty = bar_full + 8 * STAGES;          // [STAGES]
   const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;     // [kAccStages]
   const uint32_t bar_tmem_empty = bar_tmem_full + 8 * kAccStages;
-  const uint32_t tmem_slot = bar_tmem_empty + 8 * kAccStages;
-  static_assert(8 * (2 * STAGES + 2 * kAccStages) + 4 <= Cfg::BAR_BYTES, "barrier block too small");
+  const uint32_t bar_splitk = bar_tmem_empty + 8 * kAccStages;   // split-K: bulk loads of the partial slices
+  const uint32_t tmem_slot = bar_splitk + 8;
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -268,6 +279,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
       mbar_init(bar_tmem_empty + 8 * a, 4 * CG);  // one arrive per epilogue warp of every CTA in the group
     }
+    mbar_init(bar_splitk, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -290,9 +302,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     // ===== TMA producer (one thread) =====
     if (is_producer) produce(0x7fffffff);
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread of the leader CTA) =====
-    if (is_leader && elect_one()) {
+    // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
+    // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      const uint64_t desc_a0 = make_smem_desc(smem_a);
+      const uint64_t desc_b0 = make_smem_desc(smem_b);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = worker; u < num_units; u += num_workers) {
@@ -304,20 +319,25 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
-          const uint64_t da = make_smem_desc(smem_a + stage * Cfg::A_STAGE_BYTES);
-          const uint64_t db = make_smem_desc(smem_b + stage * Cfg::B_STAGE_BYTES);
+          if (elect_one()) {
+            // stage s lives (A_STAGE_BYTES >> 4) further along in the descriptor's (addr >> 4) field;
+            // +32 B per K step inside the 128 B swizzle row == +2 in that field
+            const uint64_t da = desc_a0 + uint64_t(stage * (Cfg::A_STAGE_BYTES >> 4));
+            const uint64_t db = desc_b0 + uint64_t(stage * (Cfg::B_STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // +32 B per K step inside the 128 B swizzle row == +2 in the (addr >> 4) field
-            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            // free the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
+            else umma_commit<CG>(bar_empty + 8 * stage);
+            if (kb == kb1 - 1) {   // accumulator complete: wake the epilogue
+              if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
+              else umma_commit<CG>(bar_tmem_full + 8 * acc);
+            }
           }
-          // free the smem slot (in both CTAs of a pair) once these MMAs have read it
-          if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
-          else umma_commit<CG>(bar_empty + 8 * stage);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
-        else umma_commit<CG>(bar_tmem_full + 8 * acc);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -341,7 +361,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       if constexpr (CG == 1) {
         if (splits > 1) {
           splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, tc.m_blk * kBlockM, n0, M, N,
-                               splitk_ws, splitk_ctr, c_raw);
+                               splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
