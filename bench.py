@@ -72,50 +72,90 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed regions, every few milliseconds through NVML
+    (nvidia-ml-py) from a background thread; falls back to `nvidia-smi -lms` when NVML cannot be loaded."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.proc, self.path, self.gpu = None, None, gpu_index
+        self.gpu, self.samples, self.thread, self.stop_flag, self.proc, self.path = gpu_index, [], None, False, None, None
+        self.max_mhz = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                             nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                             int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         exe = shutil.which("nvidia-smi")
         if not exe:
             return
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
-        self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                      "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen([exe, f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
+                                      str(self._physical_index())], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in Path(self.path).read_text().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
+        sm, power, reasons = [], [], set()
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            for mhz, watts, mask in self.samples:
+                sm.append(mhz); power.append(watts)
+                reasons.update(nm for bit, nm in self.REASONS.items() if mask & bit)
+            source = "nvml"
+        elif self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.path)
-        # "under load" = samples in the upper half of the observed clock range
-        load = [c for c in sm if c >= 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in Path(self.path).read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); self.max_mhz = float(f[1]); power.append(float(f[2]))
+                except (ValueError, IndexError):
+                    continue
+                reasons.update(nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active"))
+            os.unlink(self.path)
+            source = "nvidia-smi"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "neither NVML nor nvidia-smi available"}
+        # "under load" = samples taken while the board drew more than half of the highest power seen
+        load = [c for c, w in zip(sm, power) if w >= 0.5 * max(power)] if power else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load),
+                "power_w_max": max(power) if power else None, "source": source}
 
 
 def reference_cpu_step(a32, b32):

@@ -4,6 +4,7 @@
 //   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters]  CUDA-event timing (+ cuBLAS for scale)
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
+//   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
 //   dev_check grid  <acc_bits> [part nparts budget_ms]       time every config on the whole shape grid (CSV)
 //
 // Inputs are small integers, so every product and partial sum is exact in fp16 and fp32: any
@@ -314,17 +315,12 @@ static int do_grid(int acc, int part, int nparts, double budget_ms) {
 // wall: the harness metric in C++ — host wall clock around ONE call bracketed by device synchronisation
 // (reference benchmarking_utils.py:23-31), mean of per-sample TFLOP/s, our dispatcher against the six library
 // baselines (cuBLASLt auto-tuning runs the reference's 50 + 100 round search first unless rounds are given).
-static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, int tune_bench) {
-  Problem p; alloc_random(p, M, N, K);
-  __half* Brow;   // row-major B [K,N] for the NN baselines
-  CK(cudaMalloc(&Brow, size_t(K) * N * 2));
-  fill_normalish<<<g1(size_t(K) * N), 256>>>(Brow, size_t(K) * N, 0x5555u);
-  CK(cudaDeviceSynchronize());
-  if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
+static int wall_one(int acc, const Problem& p, const __half* Brow, double seconds, int tune_warm, int tune_bench) {
+  const int M = p.M, N = p.N, K = p.K;
   int cand[2] = {0, 0}; float best_ms[2] = {0, 0};
   for (int lay = 0; lay < 2; ++lay) {
     int st = b200_bl_lt_autotune_find(acc, lay, M, N, K, tune_warm, tune_bench);
-    if (st) { printf("autotune find failed %d\n", st); return 1; }
+    if (st) { printf("WALLFAIL,%d,%d,%d,%d,autotune find status %d\n", acc, M, N, K, st); return 1; }
     b200_bl_lt_autotune_info(acc, lay, &cand[lay], &best_ms[lay]);
   }
   struct Fn { const char* name; std::function<int()> f; };
@@ -343,15 +339,15 @@ static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, 
   for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
   std::mt19937 rng(12345);
   auto now = [] { return std::chrono::steady_clock::now(); };
-  for (auto& fn : fns) { if (fn.f()) { printf("warm-up call failed: %s\n", fn.name); return 1; } }
+  for (auto& fn : fns) { if (fn.f()) { printf("WALLFAIL,%d,%d,%d,%d,warm-up call failed: %s\n", acc, M, N, K, fn.name); return 1; } }
   CK(cudaDeviceSynchronize());
   int samples = 0;
-  const auto t_end = now() + std::chrono::duration<double>(seconds);
-  const auto t_warm = now() + std::chrono::duration<double>(seconds * 0.25);
-  bool warm = true;
+  const auto t_begin = now();
+  const auto t_warm = t_begin + std::chrono::duration<double>(seconds * 0.25);
+  const auto t_end = t_begin + std::chrono::duration<double>(seconds * 1.25);
   while (true) {
-    if (warm && now() > t_warm) { warm = false; }
-    if (!warm && now() > t_end + std::chrono::duration<double>(seconds * 0.25)) break;
+    const bool warm = now() < t_warm;
+    if (!warm && samples >= 3 && now() > t_end) break;
     std::shuffle(order.begin(), order.end(), rng);
     for (int id : order) {
       CK(cudaDeviceSynchronize());
@@ -369,9 +365,55 @@ static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, 
   const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
   printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3);
   fflush(stdout);
+  return 0;
+}
+
+// wall: the harness metric in C++ — host wall clock around ONE call bracketed by device synchronisation
+// (reference benchmarking_utils.py:23-31), mean of per-sample TFLOP/s, our dispatcher against the six library
+// baselines (cuBLASLt auto-tuning runs the reference's 50 + 100 round search first unless rounds are given).
+static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, int tune_bench) {
+  Problem p; alloc_random(p, M, N, K);
+  __half* Brow;   // row-major B [K,N] for the NN baselines
+  CK(cudaMalloc(&Brow, size_t(K) * N * 2));
+  fill_normalish<<<g1(size_t(K) * N), 256>>>(Brow, size_t(K) * N, 0x5555u);
+  CK(cudaDeviceSynchronize());
+  if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
+  int rc = wall_one(acc, p, Brow, seconds, tune_warm, tune_bench);
   cudaFree(Brow);
   p.release();
-  return 0;
+  return rc;
+}
+
+// wallgrid: `wall` over this process's share of the 1001-shape grid (shapes sorted by cost, dealt round-robin
+// to `nparts` processes — one per GPU), all in one process so that CUDA/cuBLAS start-up is paid once.
+static int do_wallgrid(int acc, int part, int nparts, double seconds, int tune_warm, int tune_bench, int limit) {
+  const int G[10] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384};
+  std::vector<std::array<int, 3>> shapes;
+  for (int a : G) for (int b : G) for (int c : G) shapes.push_back({a, b, c});
+  shapes.push_back({2048, 11008, 4096});
+  auto cost = [](const std::array<int, 3>& s) { return double(s[0]) * s[1] * s[2] + 3e9 * (double(s[0]) * s[1] + double(s[1]) * s[2] + double(s[0]) * s[2]) / 1e6; };
+  std::stable_sort(shapes.begin(), shapes.end(), [&](const auto& x, const auto& y) { return cost(x) > cost(y); });
+  const size_t maxe = size_t(16384) * 16384;
+  Problem p;
+  __half* Brow;
+  CK(cudaMalloc(&p.A, maxe * 2)); CK(cudaMalloc(&p.Bt, maxe * 2));
+  CK(cudaMalloc(&p.Cbuf, maxe * 2)); CK(cudaMalloc(&p.Cref, maxe * 2)); CK(cudaMalloc(&Brow, maxe * 2));
+  p.C = p.Cbuf;
+  fill_normalish<<<g1(maxe), 256>>>(p.A, maxe, 0x1234567u);
+  fill_normalish<<<g1(maxe), 256>>>(p.Bt, maxe, 0x89abcdeu);
+  fill_normalish<<<g1(maxe), 256>>>(Brow, maxe, 0x5555u);
+  CK(cudaDeviceSynchronize());
+  if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
+  int done = 0, failed = 0;
+  for (size_t si = 0; si < shapes.size(); ++si) {
+    if (int(si % nparts) != part) continue;
+    if (limit > 0 && done >= limit) break;
+    p.M = shapes[si][0]; p.N = shapes[si][1]; p.K = shapes[si][2];
+    failed += wall_one(acc, p, Brow, seconds, tune_warm, tune_bench);
+    ++done;
+  }
+  printf("WALLGRID done=%d failed=%d\n", done, failed);
+  return failed ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
@@ -389,6 +431,9 @@ int main(int argc, char** argv) {
   if (mode == "wall" && argc >= 6)
     return do_wall(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atof(argv[6]) : 1.0,
                    argc > 7 ? atoi(argv[7]) : 0, argc > 8 ? atoi(argv[8]) : 0);
+  if (mode == "wallgrid" && argc >= 5)
+    return do_wallgrid(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atof(argv[5]) : 0.3, argc > 6 ? atoi(argv[6]) : 5,
+                       argc > 7 ? atoi(argv[7]) : 15, argc > 8 ? atoi(argv[8]) : 0);
   if (mode == "grid" && argc >= 3)
     return do_grid(atoi(argv[2]), argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atof(argv[5]) : 3.0);
   printf("bad arguments\n");

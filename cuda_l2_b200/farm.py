@@ -91,6 +91,37 @@ def run_wall_engine(shape, acc_bits: int, seconds: float, tune_rounds: tuple[int
     raise RuntimeError(f"dev_check wall failed for {shape}: rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
 
 
+def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tune_rounds: tuple[int, int],
+                        gpu: int | None, out_path: Path, limit: int = 0) -> list[dict]:
+    """One process per GPU walks its share of the cost-sorted grid inside ``dev_check wallgrid`` (CUDA/cuBLAS start-up
+    and the 20 GB auto-tuning workspace are paid once per GPU instead of once per shape). The share is the
+    round-robin deal ``index % world == rank`` of the cost-sorted list — the same rule ``dev_check`` applies."""
+    exe = REPO / "cuda_l2_b200" / "lib" / "dev_check"
+    if not exe.exists():
+        raise RuntimeError(f"{exe} missing: run __graft_entry__.build() first (no fallback)")
+    env = dict(os.environ)
+    if gpu is not None:
+        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    cmd = [str(exe), "wallgrid", str(acc_bits), str(rank), str(world), str(seconds), str(tune_rounds[0]),
+           str(tune_rounds[1]), str(limit)]
+    results = []
+    with subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) as proc, \
+            open(out_path, "a") as out:
+        for line in proc.stdout:
+            if line.startswith("WALL,"):
+                rec = parse_wall_line(line)
+                rec.update(mnk=f"{rec['m']}_{rec['n']}_{rec['k']}", rank=rank, ok=True)
+            elif line.startswith("WALLFAIL,"):
+                f = line.strip().split(",")
+                rec = {"mnk": "_".join(f[2:5]), "rank": rank, "ok": False, "error": ",".join(f[5:])}
+            else:
+                continue
+            results.append(rec)
+            out.write(json.dumps(rec) + "\n")
+            out.flush()
+    return results
+
+
 def run_partition(rank: int, shapes, engine, out_path: Path | None = None, done: set | None = None) -> list[dict]:
     """Evaluate this rank's share with ``engine(shape) -> dict``; append each result to ``out_path`` (JSONL) so an
     interrupted sweep resumes where it stopped. A failing shape is recorded, not fatal (per-shape isolation)."""

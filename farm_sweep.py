@@ -30,7 +30,10 @@ def parse_args(argv=None):
     p.add_argument("--seconds", type=float, default=0.5, help="sampling time per shape (wall engine)")
     p.add_argument("--tune_rounds", default="10,30", help="cuBLASLt auto-tuning warm-up,timed rounds (reference: 50,100)")
     p.add_argument("--shapes", default="grid", help="'grid' (1000 + 2048_11008_4096) or a comma list of M_N_K")
-    p.add_argument("--limit", type=int, default=0, help="evaluate only the first N shapes of the cost-sorted list")
+    p.add_argument("--limit", type=int, default=0, help="evaluate only the first N shapes (per GPU for the wallgrid engine)")
+    p.add_argument("--engine", default="auto", choices=["auto", "wallgrid", "wall"],
+                   help="wallgrid: one dev_check process per GPU walks its share (default for --shapes grid); "
+                        "wall: one dev_check process per shape (resumable, any shape list)")
     p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
     p.add_argument("--out_dir", default=str(REPO / "eval_results"))
     p.add_argument("--mode", default="offline", choices=["offline"])
@@ -56,6 +59,9 @@ def worker(args, rank, world, gpu):
     base = Path(args.base_dir)
     base.mkdir(parents=True, exist_ok=True)
     out = base / f"worker_{args.acc_precise}_{rank}.jsonl"
+    engine_name = args.engine if args.engine != "auto" else ("wallgrid" if args.shapes == "grid" else "wall")
+    if engine_name == "wallgrid":
+        return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit)
     done = set(farm.load_done([out]))
     engine = lambda s: farm.run_wall_engine(s, bits, args.seconds, (warm, bench), gpu)
     return farm.run_partition(rank, mine, engine, out, done)
@@ -65,7 +71,7 @@ def finish(args, world):
     import bench
     base = Path(args.base_dir)
     recs = list(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))).values())
-    wanted = {"_".join(map(str, s)) for s in shape_list(args)}
+    wanted = {"_".join(map(str, s)) for s in (farm.grid_shapes() if args.shapes == "grid" else shape_list(args))}
     recs = [r for r in recs if r["mnk"] in wanted]
     peak_tf, peak_hbm, src = bench.peaks()
     acc_dir = "F32F16F16F32" if args.acc_precise == "fp32" else "F16F16F16F16"

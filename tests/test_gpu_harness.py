@@ -1,0 +1,66 @@
+"""The reference-style harness end to end on the B200: JIT-build hgemm_lib for one shape (torch extension with the
+reference's 15 exported names), run the 0/1 exactness procedure against every baseline, time one sample."""
+import json
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+EXPORTS = ["init_cublas_handle", "destroy_cublas_handle", "hgemm_cublas_nn", "hgemm_cublas_tn", "init_cublaslt_handle_v1",
+           "destroy_cublaslt_handle_v1", "hgemm_cublaslt_heuristic_nn", "hgemm_cublaslt_heuristic_tn",
+           "init_cublaslt_handle_v2", "destroy_cublaslt_handle_v2", "find_best_algo_nn_v2_torch",
+           "find_best_algo_tn_v2_torch", "hgemm_cublaslt_auto_tuning_nn", "hgemm_cublaslt_auto_tuning_tn"]
+
+
+@pytest.fixture(scope="module")
+def base_dir(tmp_path_factory):
+    return tmp_path_factory.mktemp("hgemm_jit")
+
+
+@pytest.mark.parametrize("acc", ["fp32", "fp16"])
+def test_jit_extension_exports_and_passes_zero_one(acc, base_dir):
+    from cuda_l2_b200.harness import correctness as zc
+    from cuda_l2_b200.harness.common import LibraryHandles, baseline_table, padding_for
+    from tools.utils import as_col_major, build_from_sources
+
+    mnk, (m, n, k) = "256_512_1024", (256, 512, 1024)
+    hgemm = build_from_sources(mnk=mnk, acc_precise=acc, device_type="b200", base_dir=str(base_dir / acc), verbose=False)
+    name = f"cuda_l2_b200_{acc}"
+    for sym in EXPORTS + [name]:
+        assert hasattr(hgemm, sym), sym
+    kernel = getattr(hgemm, name)
+    assert kernel.__name__ == name                       # the harness dispatches on this
+    pad = padding_for(mnk, acc, "b200")
+    assert not pad.any
+    with LibraryHandles(hgemm):
+        hgemm.find_best_algo_tn_v2_torch(m, n, k)
+        hgemm.find_best_algo_nn_v2_torch(m, n, k)
+        table = baseline_table(hgemm)
+        res = zc.run_zero_one_check(kernel_funcs=[table[x] for x in table] + [kernel], kernel_under_test_name=name,
+                                    m=m, n=n, k=k, padding=pad, device="cuda", num_iterations=3)
+    assert res.success, res.message
+    for key, val in res.result.items():
+        if key.startswith("avg_") and key.endswith("_diff"):
+            assert val == 0.0, (key, val)                # every library baseline is exact on this domain too
+    # error behaviour: C++ exception -> RuntimeError, like the reference's CHECK_TORCH_TENSOR_* macros
+    a = torch.zeros((m, k), dtype=torch.half, device="cuda")
+    b = torch.zeros((k, n), dtype=torch.half, device="cuda")
+    c = torch.zeros((m, n), dtype=torch.half, device="cuda")
+    with pytest.raises(RuntimeError):
+        kernel(a.float(), b, as_col_major(b), c)
+    with pytest.raises(RuntimeError):
+        kernel(a, b, as_col_major(b), torch.zeros((m, n + 8), dtype=torch.half, device="cuda"))
+
+
+def test_offline_benchmark_cli_writes_result(base_dir):
+    cmd = [sys.executable, str(REPO / "benchmarking_offline.py"), "--mnk", "256_512_1024", "--acc_precise", "fp32",
+           "--device_type", "b200", "--warmup_seconds", "0.2", "--benchmark_seconds", "0.5", "--base_dir",
+           str(base_dir / "fp32"), "--gpu_device_id", "0", "--perf_func", "hgemm_cublas_tn"]
+    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    rec = json.loads((base_dir / "fp32" / "benchmark_result_hgemm_cublas_tn.json").read_text())["records"]
+    assert rec["cuda_l2_b200_fp32"] > 0 and rec["hgemm_cublas_tn"] > 0 and rec["samples"] > 5
