@@ -296,6 +296,9 @@ static int do_grid(int acc, int part, int nparts, double budget_ms) {
       if (cg == 1 && nm * nn * 2 <= 148 && nkb >= 4)
         for (int sp : {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64})
           if (sp <= 148 / (nm * nn) && sp <= nkb) cands.push_back({0, sp});
+      if (cg == 1 && nkb >= 8 && nm * nn <= 148)
+        for (int cs : {2, 4, 8})
+          if (nm * nn * cs <= 296 && nkb >= 2 * cs) cands.push_back({0, -cs});   // cluster (DSMEM) split-K
       for (const auto& cand_ : cands) {
         const int gm = cand_.first, sp = cand_.second;
         if (gm > 1 && gm / 2 >= nm) continue;

@@ -202,10 +202,21 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   const int num_tiles = num_m_blocks * num_n_blocks;
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CTA_GROUP;
   if (workers < 1) workers = 1;
+  // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
+  int cluster_reduce = 0;
+  if (splits < -1) {
+    const int cs = -splits;
+    const int nkb = (K + kBlockK - 1) / kBlockK;
+    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8) && nkb >= cs) cluster_reduce = cs;
+    splits = 1;
+  }
   splits = clamp_splits<Cfg>(splits, M, N, K, workers);
   float* ws = nullptr;
   unsigned* ctr = nullptr;
-  if (splits > 1) {
+  if (cluster_reduce) {
+    workers = num_tiles * cluster_reduce;   // one cluster per tile, one CTA per k-range
+    splits = cluster_reduce;
+  } else if (splits > 1) {
     SplitKScratch* sk = nullptr;
     if ((st = splitk_scratch(di.dev, stream, &sk)) != kOk) return st;
     ws = sk->ws; ctr = sk->ctr;
@@ -222,12 +233,12 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = Cfg::CTA_GROUP;
+  attr[0].val.clusterDim.x = cluster_reduce ? cluster_reduce : Cfg::CTA_GROUP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (Cfg::CTA_GROUP > 1) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, ws, ctr,
+  cfg.numAttrs = (Cfg::CTA_GROUP > 1 || cluster_reduce) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, cluster_reduce ? 1 : 0, ws, ctr,
                                      static_cast<__half*>(C));
   return e == cudaSuccess ? kOk : int(e);
 }

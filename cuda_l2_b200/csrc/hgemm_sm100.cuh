@@ -25,6 +25,13 @@
 
 #include "ptx_sm100.cuh"
 
+#ifndef B200_MMA_SINGLE_THREAD
+#define B200_MMA_SINGLE_THREAD 0   // 1: one free-running issuing thread; 0: warp-uniform loop with an elected issuer
+#endif
+#ifndef B200_PRODUCER_PREFETCH
+#define B200_PRODUCER_PREFETCH 1    // single-CTA groups: issue the first ring of loads before the setup barrier
+#endif
+
 namespace b200 {
 
 constexpr int kBlockK = 64;          // 64 fp16 = 128 B = one swizzle row
@@ -196,6 +203,74 @@ __device__ __forceinline__ void splitk_epilogue(uint32_t taddr0, int q, int lane
   }
 }
 
+// Cluster split-K (CTA_GROUP == 1): the `splits` CTAs of a thread-block cluster share one output tile, each
+// accumulating its own k-range. Phase 1 parks the fp32 partial tile in the CTA's own (now idle) pipeline smem;
+// after a cluster barrier, CTA r sums rows [r*128/splits, (r+1)*128/splits) over all peers through distributed
+// shared memory in fixed order (deterministic), rounds once and stores to C. No global workspace, no atomics.
+__host__ __device__ constexpr uint32_t cluster_partial_row_bytes(int bn) { return uint32_t(bn) * 4u + 16u; }   // +16 B: conflict-free rows
+
+template <class Cfg>
+__device__ __forceinline__ void cluster_splitk_park(uint32_t taddr0, int q, int lane, uint32_t part_smem) {
+  using namespace ptx;
+  constexpr int BN = Cfg::BN;
+  const uint32_t row_addr = part_smem + uint32_t(q * 32 + lane) * cluster_partial_row_bytes(BN);
+#pragma unroll
+  for (int j = 0; j < BN / 32; ++j) {
+    float f[32];
+    if constexpr (Cfg::ACC_F32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr0 + j * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    } else {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32_pack16(taddr0 + (j / 2) * 64, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&v[(j & 1) * 16 + i]);
+        f[2 * i] = __low2float(h);
+        f[2 * i + 1] = __high2float(h);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      st_shared_v4f(row_addr + uint32_t(j) * 128u + uint32_t(i) * 16u, f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  }
+}
+
+template <class Cfg>
+__device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int splits, int m_base, int n0, int M, int N,
+                                                      uint32_t part_smem, __half* __restrict__ C) {
+  using namespace ptx;
+  constexpr int BN = Cfg::BN;
+  constexpr int V = BN / 4;
+  const int rows_per = kBlockM / splits;            // splits is 2, 4 or 8
+  const int r0 = split * rows_per;
+  uint32_t peer[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) peer[p] = (p < splits) ? mapa(part_smem, uint32_t(p)) : 0u;
+  for (int i = e; i < rows_per * V; i += 128) {
+    const int r = r0 + i / V, c4 = i % V;
+    const int gm = m_base + r, gn = n0 + c4 * 4;
+    if (gm >= M || gn >= N) continue;
+    const uint32_t off = uint32_t(r) * cluster_partial_row_bytes(BN) + uint32_t(c4) * 16u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if (p < splits) {
+        const float4 v = ld_dsmem_v4f(peer[p] + off);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    uint2 out;
+    out.x = pack_f16x2_rn(acc.x, acc.y);
+    out.y = pack_f16x2_rn(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kNumThreads, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, 128}
@@ -203,6 +278,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
                 const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {64, 32}
                 int M, int N, int K, int group_m,
                 int splits,                       // split-K factor; > 1 only with CTA_GROUP == 1, one unit per CTA
+                int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
                 float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (splits > 1)
                 unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
                 __half* __restrict__ c_raw        /* C base pointer, used by the split-K reduction's direct stores */) {
@@ -283,7 +359,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+#if B200_PRODUCER_PREFETCH
     if constexpr (CG == 1) produce(STAGES);   // all barriers these loads touch are this CTA's own, just initialised
+#endif
     tma_prefetch_desc(&tmap_c);
   }
   if (warp == 2) {
@@ -297,11 +375,43 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
+
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
     // ===== TMA producer (one thread) =====
     if (is_producer) produce(0x7fffffff);
   } else if (warp == 1) {
+#if B200_MMA_SINGLE_THREAD
+    // ===== MMA issuer (one free-running thread of the leader CTA) =====
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = worker; u < num_units; u += num_workers) {
+        const int kb0 = (u % splits) * kb_per_split;
+        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
+        mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after_sync();
+          const uint64_t da = make_smem_desc(smem_a + stage * Cfg::A_STAGE_BYTES);
+          const uint64_t db = make_smem_desc(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+          if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
+          else umma_commit<CG>(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
+        else umma_commit<CG>(bar_tmem_full + 8 * acc);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+#else
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
@@ -341,6 +451,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
+#endif
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
     const int q = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32q, 32q+32)
@@ -359,6 +470,11 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       tc_fence_after_sync();
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
       if constexpr (CG == 1) {
+        if (splits > 1 && cluster_reduce) {
+          cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
+          ck_m_base = tc.m_blk * kBlockM; ck_n0 = n0; ck_split = u - t * splits;
+          continue;   // the reduction runs after the cluster barrier below
+        }
         if (splits > 1) {
           splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, tc.m_blk * kBlockM, n0, M, N,
                                splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
@@ -413,6 +529,18 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  // ------------------------------------------------------------------ cluster split-K reduction
+  if constexpr (CG == 1) {
+    if (splits > 1 && cluster_reduce) {
+      __syncwarp();
+      cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
+      if (warp >= kEpiWarp0)
+        cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
+      __syncwarp();
+      cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
+    }
   }
 
   // ------------------------------------------------------------------ teardown

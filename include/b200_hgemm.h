@@ -50,8 +50,9 @@ int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
  * Returns 0 or a negative status. */
 int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* group_m, int* splits);
 /* Run one explicit configuration. group_m <= 0 and max_ctas <= 0 select the defaults; splits > 1 asks for
- * split-K (cta_group 1 configurations only; clamped so that tiles x splits fits the SMs). The split-K
- * reduction is deterministic (fixed summation order) and uses a lazily allocated per-stream workspace. */
+ * split-K through a lazily allocated per-stream fp32 workspace (cta_group 1 configurations only; clamped so
+ * that tiles x splits fits the SMs); splits = -2, -4 or -8 asks for split-K inside a thread-block cluster of that
+ * many CTAs, reduced through distributed shared memory (no workspace). Both reductions are deterministic. */
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C,
                           int M, int N, int K, int group_m, int max_ctas, int splits, void* stream);
 

@@ -38,7 +38,7 @@ def test_config_table_and_dispatch(built_libs):
         for mnk in ((64, 4096, 64), (4096, 4096, 4096), (8192, 8192, 8192), (2048, 11008, 4096), (64, 64, 64),
                     (16384, 16384, 16384), (200, 328, 72)):
             cid, gm, sp = capi.select(acc, *mnk)
-            assert cid in ids and gm >= 0 and sp >= 1
+            assert cid in ids and gm >= 0 and (sp >= 1 or sp in (-2, -4, -8))
             if mnk[0] <= 128:
                 assert cfgs[cid]["cta_group"] == 1     # a CTA pair would waste its second half on padding
 
