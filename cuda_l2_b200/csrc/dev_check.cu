@@ -238,16 +238,16 @@ static int do_sweep(int acc, int M, int N, int K, int iters) {
   const int ncfg = b200_hgemm_num_configs();
   const int gms[] = {1, 2, 4, 8, 16, 32};
   for (int c = 0; c < ncfg; ++c) {
-    int bn, st_, cg; b200_hgemm_config_info(c, &bn, &st_, &cg);
-    if (cg == 2 && M <= 128) continue;
+    int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
+    if ((M + 127) / 128 < cg * cm || (N + bn - 1) / bn < cn) continue;
     for (int gm : gms) {
-      const int nm = (M + 128 * cg - 1) / (128 * cg);
+      const int nm = (M + 128 * cg * cm - 1) / (128 * cg * cm);
       if (gm > 1 && gm / 2 >= nm) continue;   // wider than the problem: same schedule as the previous one
       int st = run_ours(acc, c, p, gm);
       cudaError_t e = cudaDeviceSynchronize();
       if (st != 0 || e != cudaSuccess) { printf("  cfg %d gm %d FAIL %d %s\n", c, gm, st, cudaGetErrorString(e)); return 1; }
       float t = time_ms([&] { run_ours(acc, c, p, gm); }, iters, 3);
-      printf("  cfg=%d (BN=%d st=%d cg=%d) gm=%-2d  %.2f us  %.1f TFLOP/s  vs cublas %.3f\n", c, bn, st_, cg, gm,
+      printf("  cfg=%d (BN=%d st=%d cg=%d cl=%dx%d) gm=%-2d  %.2f us  %.1f TFLOP/s  vs cublas %.3f\n", c, bn, st_, cg, cm, cn, gm,
              t * 1e3, flops / t * 1e-9, blas / t);
     }
   }
@@ -283,20 +283,21 @@ static int do_grid(int acc, int part, int nparts, double budget_ms) {
     std::string line;
     int best_c = -1, best_g = 0, best_s = 1; float best_t = 1e30f;
     for (int c = 0; c < ncfg; ++c) {
-      int bn, st_, cg; b200_hgemm_config_info(c, &bn, &st_, &cg);
-      if (cg == 2 && p.M <= 128) continue;
-      const int nm = (p.M + 128 * cg - 1) / (128 * cg);
-      const int nn = (p.N + bn - 1) / bn;
+      int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
+      if ((p.M + 127) / 128 < cg * cm || (p.N + bn - 1) / bn < cn) continue;   // part of the cluster would only see padding
+      const bool plain = (cm * cn == 1) && bn >= 64;
+      const int nm = (p.M + 128 * cg * cm - 1) / (128 * cg * cm);
+      const int nn = (p.N + bn * cn - 1) / (bn * cn);
       std::vector<std::pair<int, int>> cands = {{0, 1}};   // (group_m, splits)
-      if (nm * nn > 148 / cg && nm > 1 && nn > 1) {
+      if (nm * nn > 148 / (cg * cm * cn) && nm > 1 && nn > 1) {
         cands = {{1, 1}, {4, 1}, {8, 1}, {16, 1}};
         if (nm >= 32) cands.push_back({32, 1});
       }
       const int nkb = (p.K + 63) / 64;
-      if (cg == 1 && nm * nn * 2 <= 148 && nkb >= 4)
+      if (plain && cg == 1 && nm * nn * 2 <= 148 && nkb >= 4)
         for (int sp : {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64})
           if (sp <= 148 / (nm * nn) && sp <= nkb) cands.push_back({0, sp});
-      if (cg == 1 && nkb >= 8 && nm * nn <= 148)
+      if (plain && cg == 1 && nkb >= 8 && nm * nn <= 148)
         for (int cs : {2, 4, 8})
           if (nm * nn * cs <= 296 && nkb >= 2 * cs) cands.push_back({0, -cs});   // cluster (DSMEM) split-K
       for (const auto& cand_ : cands) {

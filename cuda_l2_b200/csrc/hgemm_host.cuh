@@ -58,16 +58,18 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // Row-major fp16 matrix [rows, cols] (cols contiguous) -> 2-D tiled map, 128B swizzle,
-// box = {64 columns, box_rows}. Out-of-bounds elements read as zero / are not written.
-inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
+// box = {box_cols (64 or 32) columns, box_rows}. Out-of-bounds elements read as zero / are not written.
+inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols = kBlockK) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return kNoDriver;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(cols) * 2};
-  cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
+  // the swizzle span equals the box's inner extent: 64 fp16 = 128 B, 32 fp16 = 64 B
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? kOk : kEncodeFailed;
 }
@@ -75,9 +77,9 @@ inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 // Small direct-mapped cache of encoded maps: benchmark loops re-present the same few pointers
 // (the caching allocator recycles them), and an encode costs about a microsecond of host time.
 struct MapKey {
-  const void* ptr; int rows, cols, box_rows;
+  const void* ptr; int rows, cols, box_rows, box_cols;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols;
   }
 };
 struct MapCache {
@@ -87,14 +89,14 @@ struct MapCache {
   bool valid[kSlots];
   MapCache() { std::memset(valid, 0, sizeof(valid)); }
   // Copies the map out: two operands of one call may share a slot, so a pointer into the cache would alias.
-  int get(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
-    MapKey k{ptr, rows, cols, box_rows};
+  int get(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out, int box_cols = kBlockK) {
+    MapKey k{ptr, rows, cols, box_rows, box_cols};
     uint64_t h = (reinterpret_cast<uint64_t>(ptr) >> 8) * 0x9E3779B97F4A7C15ull;
     h ^= uint64_t(uint32_t(rows)) * 0xC2B2AE3D27D4EB4Full + uint64_t(uint32_t(cols)) * 0x165667B19E3779F9ull +
-         uint64_t(box_rows);
+         uint64_t(box_rows) * 131u + uint64_t(box_cols);
     int slot = int((h >> 32) % kSlots);
     if (!(valid[slot] && keys[slot] == k)) {
-      int st = encode_2d(&maps[slot], ptr, rows, cols, box_rows);
+      int st = encode_2d(&maps[slot], ptr, rows, cols, box_rows, box_cols);
       if (st != kOk) { valid[slot] = false; return st; }
       keys[slot] = k;
       valid[slot] = true;
@@ -193,15 +195,38 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
 
   CUtensorMap ma, mb, mc;
   MapCache& cache = map_cache();
-  if ((st = cache.get(A, M, K, kBlockM, &ma)) != kOk) return st;
-  if ((st = cache.get(Bt, N, K, Cfg::LOAD_N, &mb)) != kOk) return st;
-  if ((st = cache.get(C, M, N, 32, &mc)) != kOk) return st;
+  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &ma)) != kOk) return st;
+  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &mb)) != kOk) return st;
+  if ((st = cache.get(C, M, N, 32, &mc, Cfg::EPI_N)) != kOk) return st;
 
-  const int num_m_blocks = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
-  const int num_n_blocks = (N + Cfg::BN - 1) / Cfg::BN;
+  // schedule granularity: cluster blocks of (CLUSTER_M x TILE_M) x (CLUSTER_N x BN); 1 x 1 for plain configs
+  const int num_m_blocks = (M + Cfg::TILE_M * Cfg::CLUSTER_M - 1) / (Cfg::TILE_M * Cfg::CLUSTER_M);
+  const int num_n_blocks = (N + Cfg::BN * Cfg::CLUSTER_N - 1) / (Cfg::BN * Cfg::CLUSTER_N);
   const int num_tiles = num_m_blocks * num_n_blocks;
-  int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CTA_GROUP;
+  int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CLUSTER_CTAS;
+  if constexpr (Cfg::CLUSTER_CTAS > 2) {
+    // clusters must fit inside a GPC: ask the runtime how many can be resident at once (cached per device)
+    static thread_local int max_clusters = 0, max_clusters_dev = -1;
+    if (max_clusters_dev != di.dev) {
+      cudaLaunchConfig_t probe{};
+      probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
+      probe.blockDim = dim3(kNumThreads, 1, 1);
+      probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute pa[1];
+      pa[0].id = cudaLaunchAttributeClusterDimension;
+      pa[0].val.clusterDim.x = Cfg::CLUSTER_CTAS; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+      probe.attrs = pa; probe.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, hgemm_tn_kernel<Cfg>, &probe) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = std::max(1, di.num_sms / Cfg::CLUSTER_CTAS * 7 / 8);
+      }
+      max_clusters = n; max_clusters_dev = di.dev;
+    }
+    if (max_ctas <= 0 || workers > max_clusters) workers = std::min(workers, max_clusters);
+  }
   if (workers < 1) workers = 1;
+  if (Cfg::MCAST_CTAS > 1 || Cfg::BN < 64) splits = 1;   // split-K is wired for plain configs with BN >= 64
   // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
   int cluster_reduce = 0;
   if (splits < -1) {
@@ -227,17 +252,17 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   if (group_m <= 0) group_m = (Cfg::CTA_GROUP == 2) ? 8 : 16;
 
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(workers * Cfg::CTA_GROUP), 1, 1);
+  cfg.gridDim = dim3(unsigned(workers * (cluster_reduce || splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
   cfg.blockDim = dim3(kNumThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_reduce ? cluster_reduce : Cfg::CTA_GROUP;
+  attr[0].val.clusterDim.x = cluster_reduce ? cluster_reduce : Cfg::CLUSTER_CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (Cfg::CTA_GROUP > 1 || cluster_reduce) ? 1 : 0;
+  cfg.numAttrs = (Cfg::CLUSTER_CTAS > 1 || cluster_reduce) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, cluster_reduce ? 1 : 0, ws, ctr,
                                      static_cast<__half*>(C));
   return e == cudaSuccess ? kOk : int(e);

@@ -5,10 +5,10 @@
 #pragma once
 #include "hgemm_host.cuh"
 
-#define B200_HGEMM_SHAPE_ENTRY(ACC_F32, BN, STAGES, CTA_GROUP, GROUP_M, SPLITS)                                       \
+#define B200_HGEMM_SHAPE_ENTRY(ACC_F32, BN, STAGES, CTA_GROUP, CLUSTER_M, CLUSTER_N, GROUP_M, SPLITS)                                       \
   extern "C" int b200_hgemm_shape_entry(const void* A, const void* B_kmajor, void* C, int M, int N, int K,    \
                                         void* stream) {                                                       \
-    return b200::host::launch<b200::Config<BN, STAGES, CTA_GROUP, ACC_F32>>(                                  \
+    return b200::host::launch<b200::Config<BN, STAGES, CTA_GROUP, ACC_F32, CLUSTER_M, CLUSTER_N>>(                                  \
         A, B_kmajor, C, M, N, K, static_cast<cudaStream_t>(stream), GROUP_M, 0, SPLITS);                              \
   }                                                                                                           \
   extern "C" const char* b200_hgemm_shape_strerror(int status) { return b200::host::status_string(status); }

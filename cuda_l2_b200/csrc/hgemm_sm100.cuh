@@ -25,12 +25,6 @@
 
 #include "ptx_sm100.cuh"
 
-#ifndef B200_MMA_SINGLE_THREAD
-#define B200_MMA_SINGLE_THREAD 0   // 1: one free-running issuing thread; 0: warp-uniform loop with an elected issuer
-#endif
-#ifndef B200_PRODUCER_PREFETCH
-#define B200_PRODUCER_PREFETCH 1    // single-CTA groups: issue the first ring of loads before the setup barrier
-#endif
 
 namespace b200 {
 
@@ -39,32 +33,45 @@ constexpr int kUmmaK = 16;           // K per tcgen05.mma.kind::f16
 constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
 constexpr int kNumThreads = 256;     // 8 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiChunkN = 64;       // columns per epilogue step (128 B of fp16 = one swizzle row)
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
 
-template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_>
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
   static constexpr int STAGES = STAGES_;
   static constexpr int CTA_GROUP = CTA_GROUP_; // 1: 128xBN per CTA; 2: 256xBN per CTA pair
   static constexpr bool ACC_F32 = ACC_F32_;
+  // Multicast cluster (single-CTA groups only): CLUSTER_M x CLUSTER_N CTAs work on a block of adjacent tiles;
+  // the CTAs of a cluster row share their A tile, those of a cluster column their B tile. Each CTA loads a
+  // 1/CLUSTER_N slice of A and a 1/CLUSTER_M slice of B and TMA-multicasts it to the CTAs that need it.
+  static constexpr int CLUSTER_M = CLUSTER_M_;
+  static constexpr int CLUSTER_N = CLUSTER_N_;
+  static constexpr int MCAST_CTAS = CLUSTER_M * CLUSTER_N;
+  static constexpr int CLUSTER_CTAS = CTA_GROUP * MCAST_CTAS;
   static constexpr int TILE_M = kBlockM * CTA_GROUP;
-  static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA loads per stage
+  static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA holds per stage
+  static constexpr int A_BOX_ROWS = kBlockM / CLUSTER_N;    // A rows each CTA loads per stage
+  static constexpr int B_BOX_ROWS = LOAD_N / CLUSTER_M;     // B rows each CTA loads per stage
   static constexpr int A_STAGE_BYTES = kBlockM * kBlockK * 2;
   static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BUF_BYTES = 32 * kEpiChunkN * 2;  // one warp, one chunk: 32 rows x 128 B
-  static constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;    // 4 warps x double buffer
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int EPI_N = BN < 64 ? BN : 64;            // columns per epilogue step / TMA store box
+  static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
+  static constexpr int EPI_BYTES = 4 * 2 * 32 * 64 * 2;      // 4 warps x double buffer (sized for EPI_N = 64)
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS_USED = kAccStages * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                  : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
-  static_assert(BN % kEpiChunkN == 0 && BN >= 64 && BN <= 256, "tile N must be a multiple of 64, <= 256");
-  static_assert(LOAD_N % 8 == 0 && (BN % 16) == 0, "UMMA N constraints");
+  static_assert(BN == 32 || BN % 64 == 0, "tile N is 32 or a multiple of 64");
+  static_assert(BN >= 32 && BN <= 256 && (BN % 16) == 0, "UMMA N constraints");
+  static_assert(MCAST_CTAS == 1 || CTA_GROUP == 1, "multicast clusters are built from single-CTA groups");
+  static_assert(CLUSTER_CTAS <= 8, "portable cluster size");
+  static_assert(A_BOX_ROWS % 8 == 0 && B_BOX_ROWS % 8 == 0, "slices must cover whole 8-row swizzle atoms");
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");
 };
 
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
@@ -273,18 +280,21 @@ __device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int spli
 
 template <class Cfg>
 __global__ void __launch_bounds__(kNumThreads, 1)
-hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, 128}
-                const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, LOAD_N}
-                const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {64, 32}
+hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
+                const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, B_BOX_ROWS}
+                const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {EPI_N, 32}
                 int M, int N, int K, int group_m,
-                int splits,                       // split-K factor; > 1 only with CTA_GROUP == 1, one unit per CTA
+                int splits,                       // split-K factor; > 1 only with CLUSTER_CTAS == 1, one unit per CTA
                 int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
-                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (splits > 1)
+                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K)
                 unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
-                __half* __restrict__ c_raw        /* C base pointer, used by the split-K reduction's direct stores */) {
+                __half* __restrict__ c_raw        /* C base pointer, used by the split-K reductions' direct stores */) {
   constexpr int BN = Cfg::BN;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CG = Cfg::CTA_GROUP;
+  constexpr int CM = Cfg::CLUSTER_M;
+  constexpr int CN = Cfg::CLUSTER_N;
+  constexpr bool kMcast = Cfg::MCAST_CTAS > 1;
   using namespace ptx;
 
   extern __shared__ uint8_t smem_raw[];
@@ -299,57 +309,34 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const uint32_t bar_tmem_empty = bar_tmem_full + 8 * kAccStages;
   const uint32_t bar_splitk = bar_tmem_empty + 8 * kAccStages;   // split-K: bulk loads of the partial slices
   const uint32_t tmem_slot = bar_splitk + 8;
-  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  // Position inside the cluster. Pair mode: rank 0/1 = the two CTAs of the MMA pair. Multicast mode: rank =
+  // cm + CLUSTER_M * cn. (A cluster split-K launch of a plain config also has ranks, but does not use them here.)
+  const uint32_t cluster_rank = (Cfg::CLUSTER_CTAS > 1) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = (CG == 2) ? cluster_rank : 0u;
   const bool is_leader = (cta_rank == 0);
+  const int cm = kMcast ? int(cluster_rank % CM) : 0;
+  const int cn = kMcast ? int(cluster_rank / CM) : 0;
 
-  const int num_m_blocks = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
-  const int num_n_blocks = (N + BN - 1) / BN;
+  // The schedule is over cluster blocks of (CM x TILE_M) x (CN x BN); a plain config has 1 x 1 blocks.
+  const int num_m_blocks = (M + Cfg::TILE_M * CM - 1) / (Cfg::TILE_M * CM);
+  const int num_n_blocks = (N + BN * CN - 1) / (BN * CN);
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
-  const int num_workers = gridDim.x / CG;       // CTAs (CG=1) or CTA pairs (CG=2)
-  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / Cfg::CLUSTER_CTAS;   // clusters (or single CTAs)
+  const int worker = blockIdx.x / Cfg::CLUSTER_CTAS;
   // A work unit is (tile, k-split). splits == 1: units == tiles, walked persistently. splits > 1: the host
-  // launches exactly one CTA per unit (units <= SMs), so the sibling splits of a tile are all resident.
+  // launches exactly one CTA per unit, so the sibling splits of a tile run concurrently.
   const int num_units = num_tiles * splits;
   const int kb_per_split = (num_k_blocks + splits - 1) / splits;
 
   // ------------------------------------------------------------------ one-time setup
-  // Warp 0's elected thread owns the mbarriers and is the TMA producer. Its state lives in registers across
-  // the setup barrier so that (single-CTA groups only) the first ring of loads is already in flight while
-  // TMEM is being allocated and the other warps are still arriving.
-  const bool is_producer = (warp == 0) && elect_one();
-  int p_unit = worker, p_kb = 0, p_stage = 0;
-  uint32_t p_phase = 0;
-  // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
-  const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
-  auto produce = [&](int budget) {
-    while (p_unit < num_units && budget > 0) {
-      const int t = p_unit / splits;
-      const int kb0 = (p_unit - t * splits) * kb_per_split;
-      const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
-      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM;
-      const int n0 = tc.n_blk * BN + int(cta_rank) * Cfg::LOAD_N;
-      for (; kb0 + p_kb < kb1 && budget > 0; ++p_kb, --budget) {
-        const int kb = kb0 + p_kb;
-        mbar_wait(bar_empty + 8 * p_stage, p_phase ^ 1);
-        if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * p_stage, Cfg::STAGE_BYTES * CG);
-        const uint32_t fb = full0 + 8 * p_stage;
-        tma_load_2d<CG>(smem_a + p_stage * Cfg::A_STAGE_BYTES, &tmap_a, fb, kb * kBlockK, m0);
-        tma_load_2d<CG>(smem_b + p_stage * Cfg::B_STAGE_BYTES, &tmap_b, fb, kb * kBlockK, n0);
-        if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
-      }
-      if (kb0 + p_kb >= kb1) { p_kb = 0; p_unit += num_workers; }
-    }
-  };
-  if (is_producer) {
+  if (warp == 0 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);    // producer's arrive.expect_tx (leader CTA's only, for a pair)
-      mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
+      mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx (the leader's, for a pair)
+      mbar_init(bar_empty + 8 * s, kMcast ? CM + CN - 1 : 1);   // tcgen05.commit of every CTA this stage is shared with
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
@@ -359,9 +346,6 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-#if B200_PRODUCER_PREFETCH
-    if constexpr (CG == 1) produce(STAGES);   // all barriers these loads touch are this CTA's own, just initialised
-#endif
     tma_prefetch_desc(&tmap_c);
   }
   if (warp == 2) {
@@ -370,7 +354,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
   __syncwarp();   // reconverge after the elected-lane branches before the aligned barrier
   tc_fence_before_sync();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -379,45 +363,58 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
-    // ===== TMA producer (one thread) =====
-    if (is_producer) produce(0x7fffffff);
-  } else if (warp == 1) {
-#if B200_MMA_SINGLE_THREAD
-    // ===== MMA issuer (one free-running thread of the leader CTA) =====
-    if (is_leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int u = worker; u < num_units; u += num_workers) {
-        const int kb0 = (u % splits) * kb_per_split;
-        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
-        mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
-        tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after_sync();
-          const uint64_t da = make_smem_desc(smem_a + stage * Cfg::A_STAGE_BYTES);
-          const uint64_t db = make_smem_desc(smem_b + stage * Cfg::B_STAGE_BYTES);
+    // ===== TMA producer: the warp walks the schedule, one elected lane issues =====
+    // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
+    const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
+    // multicast masks: my A slice goes to my cluster row (same cm), my B slice to my cluster column (same cn)
+    uint16_t mask_a = 0, mask_b = 0;
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
-          if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
-          else umma_commit<CG>(bar_empty + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    for (int j = 0; j < CN; ++j) mask_a |= uint16_t(1u << (cm + CM * j));
+#pragma unroll
+    for (int i = 0; i < CM; ++i) mask_b |= uint16_t(1u << (i + CM * cn));
+    const uint32_t a_slice = uint32_t(cn) * (Cfg::A_BOX_ROWS * kBlockK * 2);
+    const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
+    int stage = 0; uint32_t phase = 0;
+    for (int u = worker; u < num_units; u += num_workers) {
+      const int t = u / splits;
+      const int kb0 = (u - t * splits) * kb_per_split;
+      const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
+      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
+      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM + cn * Cfg::A_BOX_ROWS;
+      const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) {
+          if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
+          const uint32_t fb = full0 + 8 * stage;
+          const uint32_t dst_a = smem_a + stage * Cfg::A_STAGE_BYTES + a_slice;
+          const uint32_t dst_b = smem_b + stage * Cfg::B_STAGE_BYTES + b_slice;
+          if constexpr (CN > 1) tma_load_2d_mcast<CG>(dst_a, &tmap_a, fb, kb * kBlockK, m0, mask_a);
+          else tma_load_2d<CG>(dst_a, &tmap_a, fb, kb * kBlockK, m0);
+          if constexpr (CM > 1) tma_load_2d_mcast<CG>(dst_b, &tmap_b, fb, kb * kBlockK, n0, mask_b);
+          else tma_load_2d<CG>(dst_b, &tmap_b, fb, kb * kBlockK, n0);
         }
-        if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
-        else umma_commit<CG>(bar_tmem_full + 8 * acc);
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-#else
+  } else if (warp == 1) {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
       constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
       const uint64_t desc_a0 = make_smem_desc(smem_a);
       const uint64_t desc_b0 = make_smem_desc(smem_b);
+      // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
+      // into this CTA's smem, i.e. my cluster row and column (multicast mode)
+      uint16_t mask_free = 0b11;
+      if constexpr (kMcast) {
+        mask_free = 0;
+#pragma unroll
+        for (int j = 0; j < CN; ++j) mask_free |= uint16_t(1u << (cm + CM * j));
+#pragma unroll
+        for (int i = 0; i < CM; ++i) mask_free |= uint16_t(1u << (i + CM * cn));
+      }
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = worker; u < num_units; u += num_workers) {
@@ -437,8 +434,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
-            // free the smem slot (in both CTAs of a pair) once these MMAs have read it
-            if constexpr (CG == 2) umma_commit_mcast<CG>(bar_empty + 8 * stage, 0b11);
+            // free the smem slot everywhere it is shared once these MMAs have read it
+            if constexpr (CG == 2 || kMcast) umma_commit_mcast<CG>(bar_empty + 8 * stage, mask_free);
             else umma_commit<CG>(bar_empty + 8 * stage);
             if (kb == kb1 - 1) {   // accumulator complete: wake the epilogue
               if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
@@ -451,54 +448,63 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
-#endif
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
+    constexpr int EN = Cfg::EPI_N;
     const int q = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32q, 32q+32)
-    const uint32_t epi_buf0 = smem_epi + q * (2 * Cfg::EPI_BUF_BYTES);
+    const uint32_t epi_buf0 = smem_epi + q * (2 * 32 * 64 * 2);
     const uint32_t tmem_empty0 = (CG == 2) ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
-    const uint32_t row_off = uint32_t(lane) * 128u;
-    const uint32_t sw = uint32_t(lane & 7);
+    const uint32_t row_off = uint32_t(lane) * uint32_t(EN * 2);
+    // staging rows are EN*2 bytes: 128 B rows use the 128B swizzle (chunk ^= row % 8), 64 B rows the 64B one
+    const uint32_t sw = (EN == 64) ? uint32_t(lane & 7) : uint32_t((lane >> 1) & 3);
     int acc = 0; uint32_t acc_phase = 0;
     int buf = 0;
     for (int u = worker; u < num_units; u += num_workers) {
       const int t = u / splits;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m0 = tc.m_blk * Cfg::TILE_M + int(cta_rank) * kBlockM + q * 32;
-      const int n0 = tc.n_blk * BN;
+      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
+      const int m0 = m_tile0 + q * 32;
+      const int n0 = (tc.n_blk * CN + cn) * BN;
       mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
-      if constexpr (CG == 1) {
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
         if (splits > 1 && cluster_reduce) {
           cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
-          ck_m_base = tc.m_blk * kBlockM; ck_n0 = n0; ck_split = u - t * splits;
+          ck_m_base = m_tile0; ck_n0 = n0; ck_split = u - t * splits;
           continue;   // the reduction runs after the cluster barrier below
         }
         if (splits > 1) {
-          splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, tc.m_blk * kBlockM, n0, M, N,
+          splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, m_tile0, n0, M, N,
                                splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
 #pragma unroll
-      for (int j = 0; j < BN / kEpiChunkN; ++j) {
-        uint32_t packed[32];
+      for (int j = 0; j < BN / EN; ++j) {
+        uint32_t packed[EN / 2];
         if constexpr (Cfg::ACC_F32) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32b_x32(taddr0 + j * kEpiChunkN, v0);
-          tmem_ld_32x32b_x32(taddr0 + j * kEpiChunkN + 32, v1);
-          tmem_ld_wait();
+          uint32_t v0[32];
+          tmem_ld_32x32b_x32(taddr0 + j * EN, v0);
+          if constexpr (EN == 64) {
+            uint32_t v1[32];
+            tmem_ld_32x32b_x32(taddr0 + j * EN + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            packed[i] = pack_f16x2_rn(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-            packed[16 + i] = pack_f16x2_rn(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+            for (int i = 0; i < 16; ++i)
+              packed[16 + i] = pack_f16x2_rn(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          } else {
+            tmem_ld_wait();
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            packed[i] = pack_f16x2_rn(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
         } else {
-          tmem_ld_32x32b_x32_pack16(taddr0 + j * kEpiChunkN, packed);
+          if constexpr (EN == 64) tmem_ld_32x32b_x32_pack16(taddr0 + j * EN, packed);
+          else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == BN / kEpiChunkN - 1) {
+        if (j == BN / EN - 1) {
           // whole accumulator is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
@@ -512,13 +518,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         __syncwarp();
         const uint32_t dst = epi_buf0 + buf * Cfg::EPI_BUF_BYTES + row_off;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < EN / 8; ++c)
           st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1],
                        packed[4 * c + 2], packed[4 * c + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          const int nc = n0 + j * kEpiChunkN;
+          const int nc = n0 + j * EN;
           if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
             tma_store_2d(&tmap_c, epi_buf0 + buf * Cfg::EPI_BUF_BYTES, nc, m0);
           tma_store_commit();
@@ -532,7 +538,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (CG == 1) {
+  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
     if (splits > 1 && cluster_reduce) {
       __syncwarp();
       cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
@@ -546,7 +552,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   // ------------------------------------------------------------------ teardown
   __syncwarp();   // single-lane roles rejoin their warp before the aligned barrier
   tc_fence_before_sync();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);

@@ -44,6 +44,9 @@ int b200_hgemm_f16acc(const void* A, const void* B_rowmajor, const void* B_kmajo
 int b200_hgemm_num_configs(void);
 /* BN = tile N, stages = smem ring depth, cta_group = 1 (128xBN per SM) or 2 (256xBN per SM pair). */
 int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group);
+/* TMA-multicast cluster shape of a configuration (1 x 1 = none): cluster_m x cluster_n single-CTA groups work on
+ * adjacent tiles; A tiles are shared along N, B tiles along M. */
+int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n);
 /* The configuration the dispatcher uses for this problem (acc_bits = 32 or 16). */
 int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
 /* Same, also reporting the rasterisation group (0 = kernel default) and the split-K factor (1 = none).

@@ -30,9 +30,10 @@ def test_config_table_and_dispatch(built_libs):
     cfgs = capi.configs()
     assert len(cfgs) >= 5
     for c in cfgs:
-        assert c["bn"] % 64 == 0 and 64 <= c["bn"] <= 256 and c["cta_group"] in (1, 2) and c["stages"] >= 2
+        assert (c["bn"] == 32 or c["bn"] % 64 == 0) and c["bn"] <= 256 and c["cta_group"] in (1, 2) and c["stages"] >= 2
+        assert c["cta_group"] * c["cluster_m"] * c["cluster_n"] <= 8
         smem = 1024 + c["stages"] * (128 * 64 * 2 + (c["bn"] // c["cta_group"]) * 64 * 2) + 32768 + 256
-        assert smem <= 232448
+        assert smem + 256 <= 232448
     ids = {c["id"] for c in cfgs}
     for acc in ("fp32", "fp16"):
         for mnk in ((64, 4096, 64), (4096, 4096, 4096), (8192, 8192, 8192), (2048, 11008, 4096), (64, 64, 64),
