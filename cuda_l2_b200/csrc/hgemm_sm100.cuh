@@ -10,14 +10,22 @@
 // Design (nothing below is translated from the reference; it is written for Blackwell):
 //   * persistent CTAs (one per SM, or one CTA pair per 2 SMs), static tile schedule with grouped
 //     rasterisation for L2 reuse;
-//   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread),
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (warp-uniform loops, one elected lane issues),
 //     warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> swizzled smem -> TMA store);
 //   * operands land in 128B-swizzled smem via cp.async.bulk.tensor (OOB rows/cols zero-filled, so no
 //     harness padding is ever needed), consumed in place by tcgen05.mma through smem descriptors;
 //   * kStages-deep full/empty mbarrier ring between TMA and MMA, and a 2-deep TMEM accumulator ring
 //     between MMA and epilogue so the epilogue of tile i overlaps the main loop of tile i+1;
-//   * kCtaGroup == 2: cta_group::2 MMA (256 x BN per CTA pair), each CTA loads its 128 rows of A and
-//     half of the B tile, the leader CTA issues the MMAs and multicasts the commit to both CTAs.
+//   * CTA_GROUP == 2: cta_group::2 MMA (256 x BN per CTA pair), each CTA loads its 128 rows of A and
+//     half of the B tile, the leader CTA issues the MMAs and multicasts the commit to both CTAs;
+//   * CLUSTER_M x CLUSTER_N > 1: thread-block clusters of single-CTA groups on adjacent tiles. The CTAs of a
+//     cluster row need the same A tile, those of a cluster column the same B tile: each CTA loads only a
+//     1/CLUSTER_N slice of A and a 1/CLUSTER_M slice of B and TMA-multicasts it to the CTAs that need it, so the
+//     L2->SM traffic per CTA drops while every CTA still holds full tiles for its MMAs. A stage is released by
+//     a tcgen05.commit multicast to every CTA of the consumer's cluster row and column;
+//   * split-K for problems with few output tiles and long K, two flavours, both deterministic: partial tiles
+//     through an fp32 global workspace with a distributed reduction (up to 32 splits), or the splits of a tile
+//     form a cluster and reduce through distributed shared memory (2/4/8 splits, no workspace).
 #pragma once
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
