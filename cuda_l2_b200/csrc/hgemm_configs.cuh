@@ -2,7 +2,7 @@
 // generated per-shape translation units (kernels/b200_*/<M>_<N>_<K>.cu).
 //   X(id, BN, STAGES, CTA_GROUP, CLUSTER_M, CLUSTER_N)
 // Stage counts fill the 227 KB of shared memory left after the 32 KB epilogue staging area.
-// CLUSTER_M x CLUSTER_N > 1: TMA-multicast clusters of single-CTA groups (A shared along N, B along M).
+// CLUSTER_M x CLUSTER_N > 1: TMA-multicast clusters of groups (single CTAs or CTA pairs): A shared along N, B along M.
 #pragma once
 #include "hgemm_host.cuh"
 
@@ -26,8 +26,14 @@
   X(16, 64, 8, 1, 4, 1)       \
   X(17, 128, 6, 1, 2, 1)      \
   X(18, 256, 4, 1, 1, 2)      \
-  X(19, 256, 4, 1, 2, 1)
+  X(19, 256, 4, 1, 2, 1)      \
+  X(20, 256, 6, 2, 1, 2)      \
+  X(21, 256, 6, 2, 2, 1)      \
+  X(22, 128, 8, 2, 1, 2)      \
+  X(23, 128, 8, 2, 2, 1)      \
+  X(24, 192, 6, 2, 1, 2)      \
+  X(25, 192, 6, 2, 2, 1)
 
 namespace b200 {
-constexpr int kNumConfigs = 20;
+constexpr int kNumConfigs = 26;
 }

@@ -49,9 +49,10 @@ struct Config {
   static constexpr int STAGES = STAGES_;
   static constexpr int CTA_GROUP = CTA_GROUP_; // 1: 128xBN per CTA; 2: 256xBN per CTA pair
   static constexpr bool ACC_F32 = ACC_F32_;
-  // Multicast cluster (single-CTA groups only): CLUSTER_M x CLUSTER_N CTAs work on a block of adjacent tiles;
-  // the CTAs of a cluster row share their A tile, those of a cluster column their B tile. Each CTA loads a
-  // 1/CLUSTER_N slice of A and a 1/CLUSTER_M slice of B and TMA-multicasts it to the CTAs that need it.
+  // Multicast cluster: CLUSTER_M x CLUSTER_N groups (single CTAs or CTA pairs) work on a block of adjacent tiles;
+  // the groups of a cluster row share their A tile, those of a cluster column their B tile. Each CTA loads a
+  // 1/CLUSTER_N slice of its A rows and a 1/CLUSTER_M slice of its B rows and TMA-multicasts it to the CTAs
+  // (same position inside their pair) of the groups that need it. Cluster rank = (cm + CLUSTER_M * cn) * CTA_GROUP + r.
   static constexpr int CLUSTER_M = CLUSTER_M_;
   static constexpr int CLUSTER_N = CLUSTER_N_;
   static constexpr int MCAST_CTAS = CLUSTER_M * CLUSTER_N;
@@ -73,7 +74,6 @@ struct Config {
                                  : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(BN == 32 || BN % 64 == 0, "tile N is 32 or a multiple of 64");
   static_assert(BN >= 32 && BN <= 256 && (BN % 16) == 0, "UMMA N constraints");
-  static_assert(MCAST_CTAS == 1 || CTA_GROUP == 1, "multicast clusters are built from single-CTA groups");
   static_assert(CLUSTER_CTAS <= 8, "portable cluster size");
   static_assert(A_BOX_ROWS % 8 == 0 && B_BOX_ROWS % 8 == 0, "slices must cover whole 8-row swizzle atoms");
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
@@ -320,13 +320,15 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
-  // Position inside the cluster. Pair mode: rank 0/1 = the two CTAs of the MMA pair. Multicast mode: rank =
-  // cm + CLUSTER_M * cn. (A cluster split-K launch of a plain config also has ranks, but does not use them here.)
+  // Position inside the cluster: rank = (cm + CLUSTER_M * cn) * CTA_GROUP + (position inside the MMA pair).
+  // (A cluster split-K launch of a plain config also has ranks, but does not use them here.)
   const uint32_t cluster_rank = (Cfg::CLUSTER_CTAS > 1) ? cluster_ctarank() : 0u;
-  const uint32_t cta_rank = (CG == 2) ? cluster_rank : 0u;
+  const uint32_t cta_rank = cluster_rank % CG;             // position inside the MMA pair (0 for single-CTA groups)
+  const uint32_t group_rank = cluster_rank / CG;           // which group of the cluster
+  const uint32_t leader_rank = cluster_rank - cta_rank;    // cluster rank of this group's leader CTA
   const bool is_leader = (cta_rank == 0);
-  const int cm = kMcast ? int(cluster_rank % CM) : 0;
-  const int cn = kMcast ? int(cluster_rank / CM) : 0;
+  const int cm = kMcast ? int(group_rank % CM) : 0;
+  const int cn = kMcast ? int(group_rank / CM) : 0;
 
   // The schedule is over cluster blocks of (CM x TILE_M) x (CN x BN); a plain config has 1 x 1 blocks.
   const int num_m_blocks = (M + Cfg::TILE_M * CM - 1) / (Cfg::TILE_M * CM);
@@ -373,13 +375,17 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   if (warp == 0) {
     // ===== TMA producer: the warp walks the schedule, one elected lane issues =====
     // pair mode: every load of both CTAs reports its bytes to the leader's full barrier
-    const uint32_t full0 = (CG == 2) ? mapa(bar_full, 0) : bar_full;
-    // multicast masks: my A slice goes to my cluster row (same cm), my B slice to my cluster column (same cn)
+    // (multicast in pair mode: the barrier operand is the local offset with the pair-peer bit cleared, which
+    //  every destination resolves to ITS OWN pair leader — the same convention CUTLASS uses)
+    const uint32_t full_uc = (CG == 2) ? mapa(bar_full, leader_rank) : bar_full;     // unicast loads
+    const uint32_t full_mc = (CG == 2) ? (bar_full & 0xFEFFFFFFu) : bar_full;        // multicast loads
+    // multicast masks: my A slice goes to the same-position CTAs of my cluster row (same cm), my B slice to
+    // those of my cluster column (same cn)
     uint16_t mask_a = 0, mask_b = 0;
 #pragma unroll
-    for (int j = 0; j < CN; ++j) mask_a |= uint16_t(1u << (cm + CM * j));
+    for (int j = 0; j < CN; ++j) mask_a |= uint16_t(1u << ((cm + CM * j) * CG + int(cta_rank)));
 #pragma unroll
-    for (int i = 0; i < CM; ++i) mask_b |= uint16_t(1u << (i + CM * cn));
+    for (int i = 0; i < CM; ++i) mask_b |= uint16_t(1u << ((i + CM * cn) * CG + int(cta_rank)));
     const uint32_t a_slice = uint32_t(cn) * (Cfg::A_BOX_ROWS * kBlockK * 2);
     const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
     int stage = 0; uint32_t phase = 0;
@@ -394,13 +400,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
-          const uint32_t fb = full0 + 8 * stage;
           const uint32_t dst_a = smem_a + stage * Cfg::A_STAGE_BYTES + a_slice;
           const uint32_t dst_b = smem_b + stage * Cfg::B_STAGE_BYTES + b_slice;
-          if constexpr (CN > 1) tma_load_2d_mcast<CG>(dst_a, &tmap_a, fb, kb * kBlockK, m0, mask_a);
-          else tma_load_2d<CG>(dst_a, &tmap_a, fb, kb * kBlockK, m0);
-          if constexpr (CM > 1) tma_load_2d_mcast<CG>(dst_b, &tmap_b, fb, kb * kBlockK, n0, mask_b);
-          else tma_load_2d<CG>(dst_b, &tmap_b, fb, kb * kBlockK, n0);
+          if constexpr (CN > 1) tma_load_2d_mcast<CG>(dst_a, &tmap_a, full_mc + 8 * stage, kb * kBlockK, m0, mask_a);
+          else tma_load_2d<CG>(dst_a, &tmap_a, full_uc + 8 * stage, kb * kBlockK, m0);
+          if constexpr (CM > 1) tma_load_2d_mcast<CG>(dst_b, &tmap_b, full_mc + 8 * stage, kb * kBlockK, n0, mask_b);
+          else tma_load_2d<CG>(dst_b, &tmap_b, full_uc + 8 * stage, kb * kBlockK, n0);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -415,13 +420,14 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       const uint64_t desc_b0 = make_smem_desc(smem_b);
       // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
       // into this CTA's smem, i.e. my cluster row and column (multicast mode)
-      uint16_t mask_free = 0b11;
+      constexpr uint16_t kGroupBits = (CG == 2) ? 0b11 : 0b1;          // every CTA of a group
+      const uint16_t mask_self = uint16_t(kGroupBits << (group_rank * CG));
+      uint16_t mask_free = mask_self;
       if constexpr (kMcast) {
-        mask_free = 0;
 #pragma unroll
-        for (int j = 0; j < CN; ++j) mask_free |= uint16_t(1u << (cm + CM * j));
+        for (int j = 0; j < CN; ++j) mask_free |= uint16_t(kGroupBits << ((cm + CM * j) * CG));
 #pragma unroll
-        for (int i = 0; i < CM; ++i) mask_free |= uint16_t(1u << (i + CM * cn));
+        for (int i = 0; i < CM; ++i) mask_free |= uint16_t(kGroupBits << ((i + CM * cn) * CG));
       }
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -446,7 +452,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
             if constexpr (CG == 2 || kMcast) umma_commit_mcast<CG>(bar_empty + 8 * stage, mask_free);
             else umma_commit<CG>(bar_empty + 8 * stage);
             if (kb == kb1 - 1) {   // accumulator complete: wake the epilogue
-              if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, 0b11);
+              if constexpr (CG == 2) umma_commit_mcast<CG>(bar_tmem_full + 8 * acc, mask_self);
               else umma_commit<CG>(bar_tmem_full + 8 * acc);
             }
           }
@@ -461,7 +467,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     constexpr int EN = Cfg::EPI_N;
     const int q = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32q, 32q+32)
     const uint32_t epi_buf0 = smem_epi + q * (2 * 32 * 64 * 2);
-    const uint32_t tmem_empty0 = (CG == 2) ? mapa(bar_tmem_empty, 0) : bar_tmem_empty;
+    const uint32_t tmem_empty0 = (CG == 2) ? mapa(bar_tmem_empty, leader_rank) : bar_tmem_empty;
     const uint32_t row_off = uint32_t(lane) * uint32_t(EN * 2);
     // staging rows are EN*2 bytes: 128 B rows use the 128B swizzle (chunk ^= row % 8), 64 B rows the 64B one
     const uint32_t sw = (EN == 64) ? uint32_t(lane & 7) : uint32_t((lane >> 1) & 3);
