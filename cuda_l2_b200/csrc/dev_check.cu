@@ -395,7 +395,7 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
   }
   int cfg, gm, sp; b200_hgemm_select(acc, M, N, K, &cfg, &gm, &sp);
   printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0]);
-  for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.3f", fns[i].name, sum_tf[i] / samples);
+  for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.6g", fns[i].name, sum_tf[i] / samples);
   const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
   printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3);
   fflush(stdout);

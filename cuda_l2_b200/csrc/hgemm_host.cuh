@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "hgemm_sm100.cuh"
@@ -175,6 +176,11 @@ int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   return std::max(splits, 1);
 }
 
+inline bool cache_hints_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200_HGEMM_NO_CACHE_HINTS"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 // group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". splits > 1 requests
 // split-K (clamped to what the problem allows; only for CTA_GROUP == 1 configurations).
 template <class Cfg>
@@ -263,8 +269,18 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (Cfg::CLUSTER_CTAS > 1 || cluster_reduce) ? 1 : 0;
+  // L2 eviction priorities: when one operand is streamed (about) once while the other is re-read by every tile row
+  // or column and is small enough to live in L2, keep the small one and let the streamed one go first.
+  uint64_t hint_a = ptx::kL2EvictNormal, hint_b = ptx::kL2EvictNormal;
+  if (cache_hints_enabled()) {
+    const size_t a_bytes = size_t(M) * K * 2, b_bytes = size_t(N) * K * 2;
+    const int n_tiles = (N + Cfg::BN - 1) / Cfg::BN, m_tiles = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+    constexpr size_t kL2Keep = size_t(48) << 20, kStream = size_t(96) << 20;
+    if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { hint_a = ptx::kL2EvictFirst; hint_b = ptx::kL2EvictLast; }
+    else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { hint_b = ptx::kL2EvictFirst; hint_a = ptx::kL2EvictLast; }
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, cluster_reduce ? 1 : 0, ws, ctr,
-                                     static_cast<__half*>(C));
+                                     static_cast<__half*>(C), hint_a, hint_b);
   return e == cudaSuccess ? kOk : int(e);
 }
 

@@ -113,6 +113,8 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m_blocks, int num
   TileCoord c;
   c.m_blk = first_m + in_group % gsz;
   c.n_blk = in_group / gsz;
+  // serpentine: odd groups sweep N backwards, so the B panels touched last by one group are still in L2 for the next
+  if (group & 1) c.n_blk = num_n_blocks - 1 - c.n_blk;
   return c;
 }
 
@@ -296,7 +298,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
                 int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
                 float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K)
                 unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
-                __half* __restrict__ c_raw        /* C base pointer, used by the split-K reductions' direct stores */) {
+                __half* __restrict__ c_raw,       // C base pointer, used by the split-K reductions' direct stores
+                uint64_t hint_a, uint64_t hint_b  /* L2 eviction priority of the A / B loads (ptx::kL2Evict*) */) {
   constexpr int BN = Cfg::BN;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CG = Cfg::CTA_GROUP;
@@ -402,10 +405,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
           const uint32_t dst_a = smem_a + stage * Cfg::A_STAGE_BYTES + a_slice;
           const uint32_t dst_b = smem_b + stage * Cfg::B_STAGE_BYTES + b_slice;
-          if constexpr (CN > 1) tma_load_2d_mcast<CG>(dst_a, &tmap_a, full_mc + 8 * stage, kb * kBlockK, m0, mask_a);
-          else tma_load_2d<CG>(dst_a, &tmap_a, full_uc + 8 * stage, kb * kBlockK, m0);
-          if constexpr (CM > 1) tma_load_2d_mcast<CG>(dst_b, &tmap_b, full_mc + 8 * stage, kb * kBlockK, n0, mask_b);
-          else tma_load_2d<CG>(dst_b, &tmap_b, full_uc + 8 * stage, kb * kBlockK, n0);
+          if constexpr (CN > 1) tma_load_2d_mcast_hint<CG>(dst_a, &tmap_a, full_mc + 8 * stage, kb * kBlockK, m0, mask_a, hint_a);
+          else tma_load_2d_hint<CG>(dst_a, &tmap_a, full_uc + 8 * stage, kb * kBlockK, m0, hint_a);
+          if constexpr (CM > 1) tma_load_2d_mcast_hint<CG>(dst_b, &tmap_b, full_mc + 8 * stage, kb * kBlockK, n0, mask_b, hint_b);
+          else tma_load_2d_hint<CG>(dst_b, &tmap_b, full_uc + 8 * stage, kb * kBlockK, n0, hint_b);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }

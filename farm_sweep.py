@@ -37,6 +37,7 @@ def parse_args(argv=None):
     p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
     p.add_argument("--out_dir", default=str(REPO / "eval_results"))
     p.add_argument("--mode", default="offline", choices=["offline"])
+    p.add_argument("--import_wallgrid", default="", help="turn the stdout of a `dev_check wallgrid` run into the CSV reports")
     p.add_argument("--worker", type=int, default=-1, help=argparse.SUPPRESS)
     p.add_argument("--world", type=int, default=0, help=argparse.SUPPRESS)
     return p.parse_args(argv)
@@ -86,6 +87,18 @@ def finish(args, world):
 def main(argv=None):
     args = parse_args(argv)
     t0 = time.time()
+    if args.import_wallgrid:
+        base = Path(args.base_dir)
+        base.mkdir(parents=True, exist_ok=True)
+        out = base / f"worker_{args.acc_precise}_0.jsonl"
+        with open(out, "w") as f:
+            for line in Path(args.import_wallgrid).read_text().splitlines():
+                if line.startswith("WALL,"):
+                    rec = farm.parse_wall_line(line)
+                    rec.update(mnk=f"{rec['m']}_{rec['n']}_{rec['k']}", rank=0, ok=True)
+                    f.write(json.dumps(rec) + "\n")
+        finish(args, args.gpus or 1)
+        return 0
     if "RANK" in os.environ and args.worker < 0:          # under torchrun: one rank per GPU
         import torch.distributed as dist
         rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
