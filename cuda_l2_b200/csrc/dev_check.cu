@@ -353,6 +353,14 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
 static int wall_one(int acc, const Problem& p, const __half* Brow, double seconds, int tune_warm, int tune_bench) {
   const int M = p.M, N = p.N, K = p.K;
   int cand[2] = {0, 0}; float best_ms[2] = {0, 0};
+  if (tune_warm < 0) {
+    // adaptive: the reference's 50 + 100 rounds where they are cheap, fewer rounds for long kernels so that
+    // the search stays near `-tune_warm` x 10 ms per layout (assuming ~40 candidates)
+    const double est = std::max(std::max(2.0 * M * N * K / 1.2e15, 2.0 * (double(M) * K + double(N) * K + double(M) * N) / 5e12), 5e-6) + 8e-6;
+    const double budget = -tune_warm * 0.01;
+    const int rounds = std::max(6, std::min(150, int(budget / (40.0 * est))));
+    tune_warm = rounds / 3; tune_bench = rounds - tune_warm;
+  }
   for (int lay = 0; lay < 2; ++lay) {
     int st = b200_bl_lt_autotune_find(acc, lay, M, N, K, tune_warm, tune_bench);
     if (st) { printf("WALLFAIL,%d,%d,%d,%d,autotune find status %d\n", acc, M, N, K, st); return 1; }
@@ -395,7 +403,7 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
     if (!warm) ++samples;
   }
   int cfg, gm, sp; b200_hgemm_select(acc, M, N, K, &cfg, &gm, &sp);
-  printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0]);
+  printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d,tune_rounds=%d+%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0], tune_warm, tune_bench);
   for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.6g", fns[i].name, sum_tf[i] / samples);
   const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
   printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3);

@@ -67,7 +67,7 @@ def parse_wall_line(line: str) -> dict:
     assert f[0] == "WALL"
     out = {"acc": int(f[1]), "m": int(f[2]), "n": int(f[3]), "k": int(f[4])}
     for tok in f[5:]:
-        key, val = tok.split("=")
+        key, val = tok.split("=", 1)
         try:
             out[key] = float(val)
         except ValueError:
