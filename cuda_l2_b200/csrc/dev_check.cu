@@ -377,7 +377,7 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
       {"lt_auto_nn", [&] { return b200_bl_lt_autotune(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
   };
   const double flops = 2.0 * M * N * K;
-  std::vector<double> sum_tf(fns.size(), 0.0), sum_ms(fns.size(), 0.0);
+  std::vector<double> sum_tf(fns.size(), 0.0), sum_ms(fns.size(), 0.0), sum_call_ms(fns.size(), 0.0);
   std::vector<int> order(fns.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
   std::mt19937 rng(12345);
@@ -396,9 +396,10 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
       CK(cudaDeviceSynchronize());
       const auto t0 = now();
       fns[id].f();
+      const auto t_ret = now();   // the call has returned (launch enqueued), the GPU may still be running
       CK(cudaDeviceSynchronize());
       const double ms = std::chrono::duration<double, std::milli>(now() - t0).count();
-      if (!warm) { sum_tf[id] += flops / ms * 1e-9; sum_ms[id] += ms; }
+      if (!warm) { sum_tf[id] += flops / ms * 1e-9; sum_ms[id] += ms; sum_call_ms[id] += std::chrono::duration<double, std::milli>(t_ret - t0).count(); }
     }
     if (!warm) ++samples;
   }
@@ -406,7 +407,8 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
   printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d,tune_rounds=%d+%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0], tune_warm, tune_bench);
   for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.6g", fns[i].name, sum_tf[i] / samples);
   const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
-  printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3);
+  printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f,ours_call_us=%.2f,cublas_call_us=%.2f,lt_auto_call_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3,
+         sum_call_ms[0] / samples * 1e3, sum_call_ms[1] / samples * 1e3, sum_call_ms[5] / samples * 1e3);
   fflush(stdout);
   return 0;
 }

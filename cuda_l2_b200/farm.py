@@ -194,7 +194,24 @@ def write_reports(records: list[dict], out_csv: Path, peak_tflops: float, peak_g
             wins += r["speedup_vs_lt_auto_max"] >= 1.0
     n = len(ok)
     mean = sum(r["speedup_vs_lt_auto_max"] for r in ok) / n if n else float("nan")
-    return {"shapes": n, "failed": [r["mnk"] for r in records if not r.get("ok")],
+    # breakdown by roofline class at the measured peaks: launch-bound (< 1 GFLOP), tensor-bound, HBM-bound
+    classes: dict[str, list[float]] = {"launch_bound_lt_1gflop": [], "tensor_bound": [], "hbm_bound": []}
+    for r in ok:
+        m, nn_, k = (int(x) for x in r["mnk"].split("_"))
+        flops, byts = 2.0 * m * nn_ * k, 2.0 * (m * k + nn_ * k + m * nn_)
+        key = ("launch_bound_lt_1gflop" if flops < 1e9 else
+               "tensor_bound" if flops / (peak_tflops * 1e12) >= byts / (peak_gbs * 1e9) else "hbm_bound")
+        classes[key].append(r["speedup_vs_lt_auto_max"])
+    by_class = {k: {"shapes": len(v), "won": sum(x >= 1.0 for x in v), "mean_speedup": (sum(v) / len(v)) if v else None}
+                for k, v in classes.items()}
+    baseline_rows = {r["mnk"]: {"ours_tflops": r["ours"], "speedup_vs_lt_auto_max": r["speedup_vs_lt_auto_max"],
+                                "speedup_vs_cublas_max": r["ours"] / max(r["cublas_tn"], r["cublas_nn"]),
+                                "cfg": r.get("cfg"), "gm": r.get("gm"), "splits": r.get("splits")}
+                     for r in ok if r["mnk"] in ("64_4096_64", "4096_4096_4096", "8192_8192_8192", "2048_11008_4096")}
+    return {"shapes": n, "failed": [r["mnk"] for r in records if not r.get("ok")], "by_class": by_class,
+            "baseline_config_shapes": baseline_rows,
+            "won_vs_cublas_max": sum(r["ours"] >= max(r["cublas_tn"], r["cublas_nn"]) for r in ok),
+            "won_vs_lt_heuristic_max": sum(r["ours"] >= max(r["lt_heur_tn"], r["lt_heur_nn"]) for r in ok),
             "won_vs_lt_auto_max": wins, "win_fraction": wins / n if n else float("nan"), "mean_speedup_vs_lt_auto_max": mean,
             "aggregate_tflops": sum(2.0 * eval(r["mnk"].replace("_", "*")) for r in ok) /
                                 sum(2.0 * eval(r["mnk"].replace("_", "*")) / (r["ours"] * 1e12) for r in ok) * 1e-12 if n else 0.0}
