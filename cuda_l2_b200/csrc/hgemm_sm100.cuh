@@ -11,7 +11,8 @@
 //   * persistent CTAs (one per SM, or one CTA pair per 2 SMs), static tile schedule with grouped
 //     rasterisation for L2 reuse;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (warp-uniform loops, one elected lane issues),
-//     warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> swizzled smem -> TMA store);
+//     warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM -> regs -> swizzled smem -> TMA store), two warps
+//     per TMEM lane quadrant, each taking half of a tile's column chunks;
 //   * operands land in 128B-swizzled smem via cp.async.bulk.tensor (OOB rows/cols zero-filled, so no
 //     harness padding is ever needed), consumed in place by tcgen05.mma through smem descriptors;
 //   * kStages-deep full/empty mbarrier ring between TMA and MMA, and a 2-deep TMEM accumulator ring
@@ -39,7 +40,7 @@ namespace b200 {
 constexpr int kBlockK = 64;          // 64 fp16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;           // K per tcgen05.mma.kind::f16
 constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
-constexpr int kNumThreads = 256;     // 8 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
 
@@ -65,8 +66,12 @@ struct Config {
   static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_N = BN < 64 ? BN : 64;            // columns per epilogue step / TMA store box
+  static constexpr int EPI_CHUNKS = BN / EPI_N;
+  // two epilogue warps per TMEM lane quadrant share a tile's column chunks when there are at least two of them
+  static constexpr int EPI_GROUPS = EPI_CHUNKS >= 2 ? 2 : 1;
+  static constexpr int EPI_CHUNKS_PER_GROUP = (EPI_CHUNKS + EPI_GROUPS - 1) / EPI_GROUPS;
   static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
-  static constexpr int EPI_BYTES = 4 * 2 * 32 * 64 * 2;      // 4 warps x double buffer (sized for EPI_N = 64)
+  static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS_USED = kAccStages * BN;
@@ -353,7 +358,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
-      mbar_init(bar_tmem_empty + 8 * a, 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+      mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
     mbar_init(bar_splitk, 1);
     fence_mbar_init();
@@ -468,20 +473,28 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
     constexpr int EN = Cfg::EPI_N;
-    const int q = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32q, 32q+32)
-    const uint32_t epi_buf0 = smem_epi + q * (2 * 32 * 64 * 2);
+    const int q = (warp - kEpiWarp0) & 3;           // == warp % 4: TMEM lanes [32q, 32q+32)
+    const int eg = (warp - kEpiWarp0) >> 2;         // 0: first half of the column chunks, 1: second half
+    const uint32_t epi_buf = smem_epi + uint32_t(warp - kEpiWarp0) * (32 * 64 * 2);
     const uint32_t tmem_empty0 = (CG == 2) ? mapa(bar_tmem_empty, leader_rank) : bar_tmem_empty;
     const uint32_t row_off = uint32_t(lane) * uint32_t(EN * 2);
     // staging rows are EN*2 bytes: 128 B rows use the 128B swizzle (chunk ^= row % 8), 64 B rows the 64B one
     const uint32_t sw = (EN == 64) ? uint32_t(lane & 7) : uint32_t((lane >> 1) & 3);
+    constexpr int CPG = Cfg::EPI_CHUNKS_PER_GROUP;
+    const int j_begin = eg * CPG;
+    const int j_end = min(Cfg::EPI_CHUNKS, j_begin + CPG);
+    const bool working = eg < Cfg::EPI_GROUPS;      // narrow tiles keep the second set of warps idle
     int acc = 0; uint32_t acc_phase = 0;
-    int buf = 0;
+    if (working) {
     for (int u = worker; u < num_units; u += num_workers) {
       const int t = u / splits;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
       const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
       const int m0 = m_tile0 + q * 32;
       const int n0 = (tc.n_blk * CN + cn) * BN;
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+        if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
+      }
       mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
@@ -497,8 +510,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
-#pragma unroll
-      for (int j = 0; j < BN / EN; ++j) {
+      for (int j = j_begin; j < j_end; ++j) {
         uint32_t packed[EN / 2];
         if constexpr (Cfg::ACC_F32) {
           uint32_t v0[32];
@@ -521,8 +533,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == BN / EN - 1) {
-          // whole accumulator is in registers: hand the TMEM stage back to the MMA warp
+        if (j == j_end - 1) {
+          // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
@@ -530,10 +542,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
             else mbar_arrive(tmem_empty0 + 8 * acc);
           }
         }
-        // the store that last used this staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
+        // the previous store from this warp's staging buffer must have finished reading it
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        const uint32_t dst = epi_buf0 + buf * Cfg::EPI_BUF_BYTES + row_off;
+        const uint32_t dst = epi_buf + row_off;
 #pragma unroll
         for (int c = 0; c < EN / 8; ++c)
           st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1],
@@ -543,12 +555,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         if (lane == 0) {
           const int nc = n0 + j * EN;
           if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
-            tma_store_2d(&tmap_c, epi_buf0 + buf * Cfg::EPI_BUF_BYTES, nc, m0);
+            tma_store_2d(&tmap_c, epi_buf, nc, m0);
           tma_store_commit();
         }
-        buf ^= 1;
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
@@ -559,7 +571,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     if (splits > 1 && cluster_reduce) {
       __syncwarp();
       cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
-      if (warp >= kEpiWarp0)
+      if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4)
         cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
       __syncwarp();
       cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
