@@ -191,12 +191,18 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   const DeviceInfo& di = device_info();
   if (di.cc_major != 10) return kNotBlackwell;
 
-  static thread_local int attr_dev = -1;   // function attributes are per device
-  if (attr_dev != di.dev) {
+  // Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this
+  // template (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be
+  // merged across them (STB_GNU_UNIQUE) while each object still launches its own kernel copy. Key on both.
+  static thread_local int attr_dev = -1;
+  static thread_local const void* attr_fn = nullptr;
+  const void* this_fn = reinterpret_cast<const void*>(&hgemm_tn_kernel<Cfg>);
+  if (attr_dev != di.dev || attr_fn != this_fn) {
     cudaError_t e = cudaFuncSetAttribute(hgemm_tn_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return int(e);
     attr_dev = di.dev;
+    attr_fn = this_fn;
   }
 
   CUtensorMap ma, mb, mc;

@@ -67,3 +67,16 @@ def test_python_binding_rejects_cpu_tensors(built_libs):
         capi.hgemm(a, a, a)          # CPU tensors: there is no CPU fallback
     with pytest.raises(capi.B200HgemmError):
         capi.hgemm(a.float(), a, a)
+
+
+def test_library_keeps_its_template_statics_private(built_libs):
+    """libb200_hgemm.so and a JIT-built hgemm_lib.so instantiate the same templates; a process-wide (STB_GNU_UNIQUE)
+    static would let one library skip the per-kernel setup of the other (seen on the B200 as `invalid argument` on the
+    first launch after the harness ran). The build uses -fno-gnu-unique: no 'u' symbols may remain."""
+    import shutil
+    import subprocess
+    nm = shutil.which("nm")
+    if nm is None:
+        pytest.skip("nm not available")
+    out = subprocess.run([nm, "-D", str(built_libs["capi"])], capture_output=True, text=True, check=True).stdout
+    assert not [ln for ln in out.splitlines() if " u " in ln]

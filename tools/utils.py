@@ -79,6 +79,7 @@ def get_build_cuda_cflags(build_pkg: bool = False):
         "-U__CUDA_NO_HALF2_OPERATORS__",
         "--expt-relaxed-constexpr",
         "--use_fast_math",
+        "-Xcompiler=-fno-gnu-unique",   # template statics stay private to this .so (libb200_hgemm.so has its own copies)
         f"-I{PROJECT_DIR}",
         f"-I{PROJECT_DIR}/pybind",
     ]
@@ -114,7 +115,7 @@ def build_from_sources(mnk, acc_precise, device_type, base_dir: str, verbose: bo
             name="hgemm_lib",
             sources=sources,
             extra_cuda_cflags=get_build_cuda_cflags(),
-            extra_cflags=["-std=c++17", "-O2"],
+            extra_cflags=["-std=c++17", "-O2", "-fno-gnu-unique"],
             extra_ldflags=["-lcublas", "-lcublasLt"],
             verbose=verbose,
             build_directory=base_dir,
