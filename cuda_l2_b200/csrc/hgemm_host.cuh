@@ -242,9 +242,13 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
   int cluster_reduce = 0;
   if (splits < -1) {
-    const int cs = -splits;
+    int cs = -splits;
     const int nkb = (K + kBlockK - 1) / kBlockK;
-    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8) && nkb >= cs) cluster_reduce = cs;
+    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8)) {
+      // every CTA of the cluster must own at least one k-block: halve the cluster until no k-range is empty
+      while (cs > 1 && (cs - 1) * ((nkb + cs - 1) / cs) >= nkb) cs /= 2;
+      if (cs > 1) cluster_reduce = cs;
+    }
     splits = 1;
   }
   splits = clamp_splits<Cfg>(splits, M, N, K, workers);
