@@ -65,10 +65,11 @@ def peaks():
     if f.exists():
         try:
             d = json.loads(f.read_text())
-            return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)"
+            return (float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)",
+                    float(d.get("bf16_tflops_sustained", 0.0)) or None)
         except Exception:
             pass
-    return FALLBACK_TFLOPS, FALLBACK_HBM, "fallback (B200_PROFILING.md)"
+    return FALLBACK_TFLOPS, FALLBACK_HBM, "fallback (B200_PROFILING.md)", 1400.0
 
 
 class ClockSampler:
@@ -312,7 +313,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        peak_tf, peak_hbm, peak_src = peaks()
+        peak_tf, peak_hbm, peak_src, peak_sustained = peaks()
         achieved = flops_step / (ms_total / args.steps * 1e-3) * 1e-12      # per launch, from the CUDA events above
         cfg_id, group_m, splits = capi.select(args.acc, m, n, k)
         cfg = capi.configs()[cfg_id]
@@ -329,13 +330,15 @@ def main():
             "config": {"workload": f"{args.mnk} --acc_precise {args.acc} --mode offline", "parallelism": f"1 GEMM per GPU x {world}",
                        "l2_policy": f"rotating {nsets} operand sets ({nsets * set_bytes >> 20} MiB > 126 MiB L2)",
                        "kernel_config": {"tile": f"{128 * cfg['cta_group']}x{cfg['bn']}x64", "stages": cfg["stages"],
-                                         "cta_group": cfg["cta_group"], "group_m": group_m, "split_k": splits}},
+                                         "cta_group": cfg["cta_group"], "cluster": f"{cfg['cluster_m']}x{cfg['cluster_n']}", "group_m": group_m,
+                                         "split_k": splits}},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * (m * k + n * k),
                     "d2h_bytes_per_step": 2 * m * n, "steps": e2e_steps, "api": "b200_hgemm_host (pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                         "peak_sustained": peak_sustained, "frac_of_sustained": (achieved / peak_sustained) if peak_sustained else None,
                          "algorithmic_flops_per_launch": flops_step, "algorithmic_bytes_per_launch": set_bytes},
         }
         if world == 1:

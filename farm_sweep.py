@@ -74,7 +74,7 @@ def finish(args, world):
     recs = list(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))).values())
     wanted = {"_".join(map(str, s)) for s in (farm.grid_shapes() if args.shapes == "grid" else shape_list(args))}
     recs = [r for r in recs if r["mnk"] in wanted]
-    peak_tf, peak_hbm, src = bench.peaks()
+    peak_tf, peak_hbm, src, _ = bench.peaks()
     acc_dir = "F32F16F16F32" if args.acc_precise == "fp32" else "F16F16F16F16"
     out_csv = Path(args.out_dir) / f"cuda_l2_b200_{acc_dir}_speedup_{args.mode}.csv"
     summary = farm.write_reports(recs, out_csv, peak_tf, peak_hbm)

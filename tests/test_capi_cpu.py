@@ -80,3 +80,33 @@ def test_library_keeps_its_template_statics_private(built_libs):
         pytest.skip("nm not available")
     out = subprocess.run([nm, "-D", str(built_libs["capi"])], capture_output=True, text=True, check=True).stdout
     assert not [ln for ln in out.splitlines() if " u " in ln]
+
+
+def test_tuned_table_entries_are_launchable_for_every_grid_shape(built_libs):
+    """Every tuned entry must name an existing configuration whose cluster is not wider than the problem, and
+    split-K (either flavour) only on plain single-CTA configurations with tiles of at least 64 columns."""
+    from cuda_l2_b200 import farm
+    cfgs = {c["id"]: c for c in capi.configs()}
+    seen_cluster_split = seen_mcast = 0
+    for (m, n, k) in farm.grid_shapes():
+        for acc in ("fp32", "fp16"):
+            cid, gm, sp = capi.select(acc, m, n, k)
+            c = cfgs[cid]
+            assert 0 <= gm <= 64
+            assert -(-m // 128) >= c["cta_group"] * c["cluster_m"], (m, n, k, acc, c)
+            assert -(-n // c["bn"]) >= c["cluster_n"], (m, n, k, acc, c)
+            if sp != 1:
+                assert sp in (-2, -4, -8) or 2 <= sp <= 64
+                assert c["cta_group"] == 1 and c["cluster_m"] * c["cluster_n"] == 1 and c["bn"] >= 64, (m, n, k, acc, sp, c)
+                seen_cluster_split += sp < 0
+            seen_mcast += c["cluster_m"] * c["cluster_n"] > 1
+    assert seen_cluster_split > 50 and seen_mcast > 20          # the table really uses both mechanisms
+
+
+def test_off_grid_shapes_borrow_the_nearest_tuned_entry(built_libs):
+    assert capi.select("fp32", 2048, 11008, 4096) == capi.select("fp32", 2048, 11008, 4096)
+    assert capi.select("fp32", 4000, 4100, 4090) == capi.select("fp32", 4096, 4096, 4096)
+    assert capi.select("fp16", 70, 60 * 8, 16000) == capi.select("fp16", 64, 512, 16384)
+    cid, _, _ = capi.select("fp32", 8, 16, 8192)               # far off the grid in M and N: still a valid choice
+    cfg = capi.configs()[cid]
+    assert cfg["cta_group"] == 1 and cfg["cluster_m"] * cfg["cluster_n"] == 1

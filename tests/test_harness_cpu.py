@@ -148,3 +148,23 @@ def test_summarize_result_picks_harder_layout(tmp_path):
     assert rows["cuBLASLt-auto-tuning-max"]["Speedup"] == pytest.approx(1.1)
     assert rows["torch.matmul"]["Speedup"] == pytest.approx(1.5)
     assert sr.main(["--base_dir", str(tmp_path), "--acc_precise", "fp32", "--device_type", "b200"]) == 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only: one JSON line with the contract's keys."""
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--mnk", "256_512_128", "--steps", "2",
+                        "--warmup", "1"], cwd=REPO, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"].startswith("256_512_128") and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_without_a_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--steps", "1"], cwd=REPO, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
