@@ -9,6 +9,7 @@ gloo/nccl when launched under torchrun, or through per-rank JSONL files when the
 Engines:
   wall     ``dev_check wall``: the harness metric (wall clock around one call + device sync, mean TFLOP/s) in C++,
            our dispatcher vs cuBLAS / cuBLASLt-heuristic / cuBLASLt-auto-tuning, both layouts. Seconds per shape.
+  wallgrid the same, one process per GPU walking its whole share (start-up paid once) — the default for the full grid.
   harness  the reference-style ``eval_one_file.sh`` (JIT build + 1 correctness + 7 benchmark processes). Minutes per shape.
 """
 from __future__ import annotations
@@ -89,6 +90,46 @@ def run_wall_engine(shape, acc_bits: int, seconds: float, tune_rounds: tuple[int
         if line.startswith("WALL,"):
             return parse_wall_line(line)
     raise RuntimeError(f"dev_check wall failed for {shape}: rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+
+
+HARNESS_KEYS = {"torch.matmul": "matmul", "cuBLAS-tn": "cublas_tn", "cuBLAS-nn": "cublas_nn",
+                "cuBLASLt-heuristic-tn": "lt_heur_tn", "cuBLASLt-heuristic-nn": "lt_heur_nn",
+                "cuBLASLt-auto-tuning-tn": "lt_auto_tn", "cuBLASLt-auto-tuning-nn": "lt_auto_nn"}
+
+
+def record_from_harness_summary(summary: dict) -> dict:
+    """{base_dir}/summary.json of one eval_one_file.sh run (written by summarize_result.py) -> a sweep record.
+    Every baseline process timed the kernel again; `ours` is their mean, each baseline keeps its own pairing through
+    the stored speed-ups, so the "-max" columns are exactly the harness's."""
+    rec, ours = {}, []
+    for name, key in HARNESS_KEYS.items():
+        row = summary[name]
+        ours.append(row["CUDA-L2 TFLOPS"])
+        rec[key + "_speedup"] = row["Speedup"]
+    rec["ours"] = sum(ours) / len(ours)
+    for key in HARNESS_KEYS.values():          # baselines re-expressed against the common `ours`
+        rec[key] = rec["ours"] / rec[key + "_speedup"]
+    rec["speedup_vs_lt_auto_max"] = min(rec["lt_auto_tn_speedup"], rec["lt_auto_nn_speedup"])
+    return rec
+
+
+def run_harness_engine(shape, acc_precise: str, warmup_s: float, bench_s: float, gpu: int | None, base_dir: Path,
+                       mode: str = "offline", target_qps: float | None = None) -> dict:
+    """The reference-style flow for one shape: eval_one_file.sh (JIT build, 0/1 check, 7 baseline processes, summary)."""
+    m, n, k = shape
+    env = dict(os.environ)
+    if gpu is not None:
+        env["CUDA_VISIBLE_DEVICES"] = str(gpu)      # the worker then addresses its GPU as device 0
+    out = Path(base_dir) / f"{m}_{n}_{k}"
+    cmd = [str(REPO / "eval_one_file.sh"), "--mnk", f"{m}_{n}_{k}", "--acc_precise", acc_precise, "--device_type", "b200",
+           "--warmup_seconds", str(warmup_s), "--benchmark_seconds", str(bench_s), "--base_dir", str(out),
+           "--gpu_device_id", "0", "--mode", mode]
+    if mode == "server":
+        cmd += ["--target_qps", str(target_qps or 100)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3600)
+    if r.returncode != 0:
+        raise RuntimeError(f"eval_one_file.sh failed for {shape}: rc={r.returncode}\n{r.stdout[-1500:]}\n{r.stderr[-1500:]}")
+    return record_from_harness_summary(json.loads((out / "summary.json").read_text()))
 
 
 def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tune_rounds: tuple[int, int],

@@ -31,9 +31,10 @@ def parse_args(argv=None):
     p.add_argument("--tune_rounds", default="10,30", help="cuBLASLt auto-tuning warm-up,timed rounds (reference: 50,100)")
     p.add_argument("--shapes", default="grid", help="'grid' (1000 + 2048_11008_4096) or a comma list of M_N_K")
     p.add_argument("--limit", type=int, default=0, help="evaluate only the first N shapes (per GPU for the wallgrid engine)")
-    p.add_argument("--engine", default="auto", choices=["auto", "wallgrid", "wall"],
+    p.add_argument("--engine", default="auto", choices=["auto", "wallgrid", "wall", "harness"],
                    help="wallgrid: one dev_check process per GPU walks its share (default for --shapes grid); "
-                        "wall: one dev_check process per shape (resumable, any shape list)")
+                        "wall: one dev_check process per shape (resumable, any shape list); "
+                        "harness: eval_one_file.sh per shape (--seconds = benchmark seconds, warm-up = half of it)")
     p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
     p.add_argument("--out_dir", default=str(REPO / "eval_results"))
     p.add_argument("--mode", default="offline", choices=["offline"])
@@ -55,7 +56,7 @@ def shape_list(args):
 
 def worker(args, rank, world, gpu):
     bits = 32 if args.acc_precise == "fp32" else 16
-    warm, bench = (int(x) for x in args.tune_rounds.split(","))
+    warm, bench = (int(x) for x in args.tune_rounds.split(",")) if "," in args.tune_rounds else (-25, 0)
     mine = farm.partition(shape_list(args), world)[rank]
     base = Path(args.base_dir)
     base.mkdir(parents=True, exist_ok=True)
@@ -64,7 +65,10 @@ def worker(args, rank, world, gpu):
     if engine_name == "wallgrid":
         return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit)
     done = set(farm.load_done([out]))
-    engine = lambda s: farm.run_wall_engine(s, bits, args.seconds, (warm, bench), gpu)
+    if engine_name == "harness":
+        engine = lambda s: farm.run_harness_engine(s, args.acc_precise, args.seconds / 2, args.seconds, gpu, base / "harness")
+    else:
+        engine = lambda s: farm.run_wall_engine(s, bits, args.seconds, (warm, bench), gpu)
     return farm.run_partition(rank, mine, engine, out, done)
 
 

@@ -90,3 +90,15 @@ def test_two_rank_gloo_sweep_gathers_everything_on_rank0(tmp_path):
     got = json.loads(out.read_text())
     assert got["n"] == 27 and got["ranks"] == [0, 1]
     assert got["keys"] == sorted("_".join(map(str, s)) for s in farm.grid_shapes() if max(s) <= 256)
+
+
+def test_harness_summary_becomes_a_sweep_record():
+    summary = {name: {"Baseline Method Name": name, "Baseline TFLOPS": base, "CUDA-L2 TFLOPS": ours, "Speedup": ours / base}
+               for name, base, ours in [("torch.matmul", 80.0, 120.0), ("cuBLAS-tn", 100.0, 120.0), ("cuBLAS-nn", 90.0, 117.0),
+                                        ("cuBLASLt-heuristic-tn", 100.0, 121.0), ("cuBLASLt-heuristic-nn", 100.0, 119.0),
+                                        ("cuBLASLt-auto-tuning-tn", 110.0, 121.0), ("cuBLASLt-auto-tuning-nn", 125.0, 120.0)]}
+    rec = farm.record_from_harness_summary(summary)
+    assert rec["speedup_vs_lt_auto_max"] == pytest.approx(120.0 / 125.0)
+    row = farm.speedup_row("64_64_64", rec)
+    assert row["cuBLAS-tn"] == pytest.approx(1.2) and row["cuBLAS-max"] == pytest.approx(1.2)     # tn is the harder layout
+    assert row["cuBLASLt-auto-tuning-max"] == pytest.approx(0.96) and row["torch.matmul"] == pytest.approx(1.5)
