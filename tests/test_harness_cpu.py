@@ -168,3 +168,45 @@ def test_bench_without_a_gpu_fails_loudly():
         pytest.skip("GPU present")
     r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--steps", "1"], cwd=REPO, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_attestation_catches_the_five_attacks_of_defense_py():
+    """CPU restatement of the reference's self-tests (defense.py:336-579): a legitimate kernel passes, a thread
+    spawner, an output replacer / no-op, a dtype changer and a patched timer are each caught."""
+    import threading
+    import time as _time
+
+    from cuda_l2_b200.harness import attestation as at
+    name = "cuda_l2_b200_fp32"
+    legit = zc.cpu_stand_in(name)
+    a = torch.randn(64, 64).half(); b = torch.randn(64, 64).half()
+    bt = utils.as_col_major(b); c = torch.empty(64, 64, dtype=torch.half)
+    v = at.attest(legit, a, b, bt, c)
+    assert v.passed, v.checks
+
+    stop = threading.Event()
+    def spawner(a, b, bt, c):
+        legit(a, b, bt, c)
+        threading.Thread(target=stop.wait, daemon=True).start()
+    v = at.attest(spawner, a, b, bt, c)
+    stop.set()
+    assert not v.passed and not dict((n, p) for n, p, _ in v.checks)["no_new_threads"]
+
+    v = at.attest(lambda a, b, bt, c: None, a, b, bt, c)                      # never writes c
+    assert not dict((n, p) for n, p, _ in v.checks)["real_output"]
+
+    def retyper(a, b, bt, c):
+        legit(a, b, bt, c)
+        c.data = c.data.float()                                              # "precision downgrade" in reverse: not fp16 any more
+    c2 = torch.empty(64, 64, dtype=torch.half)
+    v = at.attest(retyper, a, b, bt, c2)
+    assert not v.passed
+
+    real = _time.perf_counter
+    try:
+        _time.perf_counter = lambda: 0.0
+        ok, msg = at.check_timers_unpatched()
+        assert not ok and "perf_counter" in msg
+    finally:
+        _time.perf_counter = real
+    assert at.check_timers_unpatched()[0]

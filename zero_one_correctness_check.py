@@ -6,6 +6,8 @@ Same CLI as the reference's zero_one_correctness_check.py (:19-25) with --device
                     is filled by a CPU stand-in that reads the same operands, so generator, K-major layout,
                     guard bands, mask and verdict are exercised end to end
   --iterations N    cap on iterations (default 100, as in the reference)
+  --attest          also run the five timing-integrity checks of the reference's defense.py on the kernel (no hidden
+                    streams or threads, real fp16 output, genuine timers) and store the verdict in the result file
 Exit status is 1 when the check fails (the reference always exits 0). Logic: cuda_l2_b200/harness/correctness.py.
 """
 import argparse
@@ -25,6 +27,7 @@ def main(argv=None) -> int:
     add_common_args(p)
     p.add_argument("--device", choices=["cuda", "cpu"], default="cuda")
     p.add_argument("--iterations", type=int, default=100)
+    p.add_argument("--attest", action="store_true")
     args = p.parse_args(argv)
     torch.set_grad_enabled(False)
     seed_everything(args.seed)
@@ -58,6 +61,16 @@ def main(argv=None) -> int:
                 import traceback
                 traceback.print_exc()
                 res = zc.CheckResult(False, str(e), {})
+    if args.attest and args.device == "cuda" and res.success:
+        from cuda_l2_b200.harness.attestation import attest
+        from tools.utils import as_col_major
+        a = torch.randn((m, k), device="cuda").half()
+        b = torch.randn((k, n), device="cuda").half()
+        verdict = attest(kernel, a, b, as_col_major(b), torch.empty((m, n), dtype=torch.half, device="cuda"))
+        res.result["attestation"] = verdict.to_json()
+        print("Attestation:", verdict.to_json())
+        if not verdict.passed:
+            res = zc.CheckResult(False, "timing-integrity attestation failed", res.result)
     print(res.result)
     zc.write_result(args.base_dir, res)
     print("Correctness Check PASSED:" if res.success else "Correctness Check FAILED:", res.message)
