@@ -259,9 +259,14 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     splits = cluster_reduce;
   } else if (splits > 1) {
     SplitKScratch* sk = nullptr;
-    if ((st = splitk_scratch(di.dev, stream, &sk)) != kOk) return st;
-    ws = sk->ws; ctr = sk->ctr;
-    workers = num_tiles * splits;          // exactly one CTA per (tile, split) unit
+    if (splitk_scratch(di.dev, stream, &sk) == kOk) {
+      ws = sk->ws; ctr = sk->ctr;
+      workers = num_tiles * splits;        // exactly one CTA per (tile, split) unit
+    } else {
+      cudaGetLastError();
+      splits = 1;                          // no scratch (allocation failed / more than 8 streams): run unsplit
+      if (workers > num_tiles) workers = num_tiles;
+    }
   } else if (workers > num_tiles) {
     workers = num_tiles;
   }

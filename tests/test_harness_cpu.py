@@ -210,3 +210,27 @@ def test_attestation_catches_the_five_attacks_of_defense_py():
     finally:
         _time.perf_counter = real
     assert at.check_timers_unpatched()[0]
+
+
+def test_generated_kernel_sources_compile_for_sm100a(tmp_path):
+    """The per-shape translation units the JIT harness builds: one of each flavour (single CTA, CTA pair, multicast
+    cluster, cluster split-K, workspace split-K if present, BN = 32) must compile on their own with nvcc."""
+    import re
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    wanted = {"pair": r"cta_group\*/ 2,", "cluster": r"/\*cluster\*/ (?!1, 1)", "csplit": r"split-K\*/ -", "bn32": r"tile N\*/ 32,",
+              "plain": r"cta_group\*/ 1, /\*cluster\*/ 1, 1, /\*group_m\*/ \d+, /\*split-K\*/ 1\)"}
+    picked = {}
+    for d in ("b200_F32F16F16F32", "b200_F16F16F16F16"):
+        for f in sorted((REPO / "kernels" / d).glob("*.cu")):
+            text = f.read_text()
+            for tag, pat in wanted.items():
+                if (d, tag) not in picked and re.search(pat, text):
+                    picked[(d, tag)] = f
+    assert {t for _, t in picked} == set(wanted), picked.keys()
+    for (d, tag), f in list(picked.items())[:8]:
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", f"-I{REPO}", "-c", str(f),
+                            "-o", str(tmp_path / f"{d}_{tag}.o")], capture_output=True, text=True)
+        assert r.returncode == 0, (f.name, r.stderr[-1500:])
