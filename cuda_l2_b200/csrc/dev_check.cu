@@ -5,7 +5,8 @@
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
 //   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
-//   dev_check grid  <acc_bits> [part nparts budget_ms min_gflop max_gflop]       time every config on the whole shape grid (CSV)
+//   dev_check grid  <acc_bits> [part nparts budget_ms min_gflop max_gflop [wall]]  time every config on the whole shape grid (CSV);
+//                                                     "wall": rank by the harness metric instead of CUDA-event time
 //
 // Inputs are small integers, so every product and partial sum is exact in fp16 and fp32: any
 // mismatch is a kernel bug, never rounding. C is surrounded by guard bands to catch stray writes.
@@ -269,7 +270,11 @@ static int do_sweep(int acc, int M, int N, int K, int iters) {
 
 // grid: time every configuration on every shape of the harness grid (+ the extra LLM shape); one CSV line per
 // shape:  M,N,K,cublas_us,best_cfg,best_gm,best_us,<cfg>:<gm>:<us>...   Used by tools/tune_b200.py.
-static int do_grid(int acc, int part, int nparts, double budget_ms, double min_gflop = 0.0, double max_gflop = 1e30) {
+// wall_metric: time each launch the way the harness does (host clock around one call bracketed by device
+// synchronisation, reference benchmarking_utils.py:23-31) and rank candidates by their mean TFLOP/s over the rounds —
+// the quantity the sweep is scored on — instead of the median CUDA-event time of the isolated launch.
+static int do_grid(int acc, int part, int nparts, double budget_ms, double min_gflop = 0.0, double max_gflop = 1e30,
+                   bool wall_metric = false) {
   const int G[10] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384};
   std::vector<std::array<int, 3>> shapes;
   for (int a : G) for (int b : G) for (int c : G) shapes.push_back({a, b, c});
@@ -326,14 +331,32 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     // them see the same clock / thermal state — what the harness's alternating calls see.
     std::vector<float> blas_t;
     cudaEvent_t ea, eb; CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
-    auto once = [&](auto&& f) { CK(cudaEventRecord(ea)); f(); CK(cudaEventRecord(eb)); CK(cudaEventSynchronize(eb)); float ms; CK(cudaEventElapsedTime(&ms, ea, eb)); return ms; };
+    auto once = [&](auto&& f) {
+      float ms;
+      if (wall_metric) {
+        CK(cudaDeviceSynchronize());
+        const auto t0 = std::chrono::steady_clock::now();
+        f();
+        CK(cudaDeviceSynchronize());
+        ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      } else {
+        CK(cudaEventRecord(ea)); f(); CK(cudaEventRecord(eb)); CK(cudaEventSynchronize(eb));
+        CK(cudaEventElapsedTime(&ms, ea, eb));
+      }
+      return ms;
+    };
     for (int r = 0; r < iters + 1; ++r) {
       const float tb = once([&] { cublas_tn(p, p.Cref); });
       if (r) blas_t.push_back(tb);
       for (auto& cd : all) { const float t = once([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
     }
     cudaEventDestroy(ea); cudaEventDestroy(eb);
-    auto med = [](std::vector<float>& v) { std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
+    // event metric: median time; wall metric: the time whose rate is the mean rate (the harness averages TFLOP/s)
+    auto med = [&](std::vector<float>& v) {
+      if (wall_metric) { double r = 0; for (float t : v) r += 1.0 / t; return float(v.size() / r); }
+      std::sort(v.begin(), v.end());
+      return v[v.size() / 2];
+    };
     blas = med(blas_t);
     for (auto& cd : all) {
       const float t = med(cd.t);
@@ -481,7 +504,8 @@ int main(int argc, char** argv) {
     return do_wallgrid(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atof(argv[5]) : 0.3, argc > 6 ? atoi(argv[6]) : 5,
                        argc > 7 ? atoi(argv[7]) : 15, argc > 8 ? atoi(argv[8]) : 0);
   if (mode == "grid" && argc >= 3)
-    return do_grid(atoi(argv[2]), argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atof(argv[5]) : 3.0, argc > 6 ? atof(argv[6]) : 0.0, argc > 7 ? atof(argv[7]) : 1e30);
+    return do_grid(atoi(argv[2]), argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atof(argv[5]) : 3.0, argc > 6 ? atof(argv[6]) : 0.0, argc > 7 ? atof(argv[7]) : 1e30,
+                   argc > 8 && std::string(argv[8]) == "wall");
   printf("bad arguments\n");
   return 64;
 }
