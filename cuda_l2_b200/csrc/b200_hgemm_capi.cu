@@ -141,6 +141,35 @@ int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* h
   return e == cudaSuccess ? 0 : int(e);
 }
 
+#ifdef B200_HGEMM_TRACE
+// Developer-only entry points of libb200_hgemm_trace.so (see kTraceSlots in hgemm_sm100.cuh); not part of the C ABI.
+static unsigned long long* g_trace_dev = nullptr;
+static int g_trace_ctas = 0;
+int b200_hgemm_trace_slots(void) { return b200::kTraceSlots; }
+int b200_hgemm_trace_arm(int max_ctas) {   // zero the buffer and point the kernels at it (max_ctas <= 0: disarm)
+  unsigned long long* none = nullptr;
+  if (max_ctas <= 0) return int(cudaMemcpyToSymbol(b200::g_trace_buf, &none, sizeof(none)));
+  const size_t bytes = size_t(max_ctas) * b200::kTraceSlots * 2 * sizeof(unsigned long long);
+  if (max_ctas > g_trace_ctas) {
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    g_trace_dev = nullptr; g_trace_ctas = 0;
+    cudaError_t e = cudaMalloc(&g_trace_dev, bytes);
+    if (e != cudaSuccess) return int(e);
+    g_trace_ctas = max_ctas;
+  }
+  cudaError_t e = cudaMemset(g_trace_dev, 0, bytes);
+  if (e != cudaSuccess) return int(e);
+  return int(cudaMemcpyToSymbol(b200::g_trace_buf, &g_trace_dev, sizeof(g_trace_dev)));
+}
+int b200_hgemm_trace_read(unsigned long long* out, int ctas) {
+  if (!g_trace_dev || ctas > g_trace_ctas) return b200::host::kBadShape;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return int(e);
+  return int(cudaMemcpy(out, g_trace_dev, size_t(ctas) * b200::kTraceSlots * 2 * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost));
+}
+#endif
+
 unsigned long long b200_hgemm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* b200_hgemm_strerror(int status) { return b200::host::status_string(status); }

@@ -44,6 +44,35 @@ constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
 
+// Developer instrumentation (only in builds with -DB200_HGEMM_TRACE, i.e. libb200_hgemm_trace.so; the product build
+// contains none of it): per-CTA timestamps of the kernel's phases, read back by `dev_check_trace trace`.
+//   slot 0 entry | 1 setup done | 2 first TMA issued | 3 last TMA issued | 4 first stage landed (MMA warp)
+//   5 last MMA commit issued | 6 first accumulator complete (epilogue) | 7 epilogue drained | 8 after the teardown
+//   barrier | 9 k-blocks issued (a count) | 10 last accumulator complete (epilogue) | 11 units run (a count)
+constexpr int kTraceSlots = 12;      // each slot: {%globaltimer ns, clock64}
+#ifdef B200_HGEMM_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;   // [gridDim.x][kTraceSlots][2], zeroed by the host before the launch
+__device__ __forceinline__ void trace_mark(int slot) {
+  if (g_trace_buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* e = g_trace_buf + (size_t(blockIdx.x) * kTraceSlots + slot) * 2;
+    e[0] = t;
+    e[1] = (unsigned long long)clock64();
+  }
+}
+__device__ __forceinline__ void trace_value(int slot, unsigned long long v) {
+  if (g_trace_buf) g_trace_buf[(size_t(blockIdx.x) * kTraceSlots + slot) * 2] = v;
+}
+#define B200_TRACE(slot) ::b200::trace_mark(slot)
+#define B200_TRACE_VALUE(slot, v) ::b200::trace_value(slot, v)
+#define B200_TRACE_ONLY(...) __VA_ARGS__
+#else
+#define B200_TRACE(slot) ((void)0)
+#define B200_TRACE_VALUE(slot, v) ((void)0)
+#define B200_TRACE_ONLY(...)
+#endif
+
 template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
@@ -328,6 +357,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(0);)
   // Position inside the cluster: rank = (cm + CLUSTER_M * cn) * CTA_GROUP + (position inside the MMA pair).
   // (A cluster split-K launch of a plain config also has ranks, but does not use them here.)
   const uint32_t cluster_rank = (Cfg::CLUSTER_CTAS > 1) ? cluster_ctarank() : 0u;
@@ -376,6 +406,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
   int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
 
@@ -397,6 +428,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const uint32_t a_slice = uint32_t(cn) * (Cfg::A_BOX_ROWS * kBlockK * 2);
     const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
     int stage = 0; uint32_t phase = 0;
+    B200_TRACE_ONLY(bool trace_first = true;)
     for (int u = worker; u < num_units; u += num_workers) {
       const int t = u / splits;
       const int kb0 = (u - t * splits) * kb_per_split;
@@ -414,11 +446,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tma_load_2d_hint<CG>(dst_a, &tmap_a, full_uc + 8 * stage, kb * kBlockK, m0, hint_a);
           if constexpr (CM > 1) tma_load_2d_mcast_hint<CG>(dst_b, &tmap_b, full_mc + 8 * stage, kb * kBlockK, n0, mask_b, hint_b);
           else tma_load_2d_hint<CG>(dst_b, &tmap_b, full_uc + 8 * stage, kb * kBlockK, n0, hint_b);
+          B200_TRACE_ONLY(if (trace_first) { B200_TRACE(2); trace_first = false; })
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    B200_TRACE_ONLY(if (lane == 0) B200_TRACE(3);)
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
@@ -439,6 +473,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      B200_TRACE_ONLY(bool trace_first = true; unsigned long long trace_kb = 0, trace_units = 0;)
       for (int u = worker; u < num_units; u += num_workers) {
         const int kb0 = (u % splits) * kb_per_split;
         const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
@@ -448,6 +483,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
+          B200_TRACE_ONLY(if (trace_first) { if (lane == 0) B200_TRACE(4); trace_first = false; } ++trace_kb;)
           if (elect_one()) {
             // stage s lives (A_STAGE_BYTES >> 4) further along in the descriptor's (addr >> 4) field;
             // +32 B per K step inside the 128 B swizzle row == +2 in that field
@@ -468,7 +504,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        B200_TRACE_ONLY(++trace_units;)
       }
+      B200_TRACE_ONLY(if (lane == 0) { B200_TRACE(5); B200_TRACE_VALUE(9, trace_kb); B200_TRACE_VALUE(11, trace_units); })
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
@@ -485,6 +523,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const int j_end = min(Cfg::EPI_CHUNKS, j_begin + CPG);
     const bool working = eg < Cfg::EPI_GROUPS;      // narrow tiles keep the second set of warps idle
     int acc = 0; uint32_t acc_phase = 0;
+    B200_TRACE_ONLY(bool trace_first = true;)
     if (working) {
     for (int u = worker; u < num_units; u += num_workers) {
       const int t = u / splits;
@@ -497,6 +536,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
       tc_fence_after_sync();
+      B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) { if (trace_first) { B200_TRACE(6); trace_first = false; } B200_TRACE(10); })
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
       if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
         if (splits > 1 && cluster_reduce) {
@@ -564,6 +604,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
+    B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) B200_TRACE(7);)
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
@@ -582,6 +623,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   __syncwarp();   // single-lane roles rejoin their warp before the aligned barrier
   tc_fence_before_sync();
   if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(8);)
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
