@@ -332,24 +332,50 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     // them see the same clock / thermal state — what the harness's alternating calls see.
     std::vector<float> blas_t;
     cudaEvent_t ea, eb; CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
-    auto once = [&](auto&& f) {
+    auto once_event = [&](auto&& f) {
       float ms;
-      if (wall_metric) {
-        CK(cudaDeviceSynchronize());
-        const auto t0 = std::chrono::steady_clock::now();
-        f();
-        CK(cudaDeviceSynchronize());
-        ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-      } else {
-        CK(cudaEventRecord(ea)); f(); CK(cudaEventRecord(eb)); CK(cudaEventSynchronize(eb));
-        CK(cudaEventElapsedTime(&ms, ea, eb));
-      }
+      CK(cudaEventRecord(ea)); f(); CK(cudaEventRecord(eb)); CK(cudaEventSynchronize(eb));
+      CK(cudaEventElapsedTime(&ms, ea, eb));
       return ms;
     };
-    for (int r = 0; r < iters + 1; ++r) {
-      const float tb = once([&] { cublas_tn(p, p.Cref); });
-      if (r) blas_t.push_back(tb);
-      for (auto& cd : all) { const float t = once([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
+    auto once_wall = [&](auto&& f) {
+      CK(cudaDeviceSynchronize());
+      const auto t0 = std::chrono::steady_clock::now();
+      f();
+      CK(cudaDeviceSynchronize());
+      return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    auto median = [](std::vector<float> v) { std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
+    if (wall_metric) {
+      // Two phases. A rotation through ~40 candidates, most of them far from the best, leaves the chip below its power
+      // cap, and the ranking of the good ones in that state is not their ranking in the harness, whose rotation holds
+      // only efficient kernels (ours + six cuBLAS flavours) and sits at the cap: in round 1 the event-time tuner
+      // preferred 128x256 single-CTA tiles on many large shapes where the 256x256 CTA-pair tile is 2-5 % better in
+      // the harness. So: a quick event-time pass shortlists, the shortlist is ranked in a harness-like rotation.
+      const int quick = std::max(2, iters / 4);
+      for (int r = 0; r < quick + 1; ++r)
+        for (auto& cd : all) { const float t = once_event([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
+      std::sort(all.begin(), all.end(), [&](const Cand& x, const Cand& y) { return median(x.t) < median(y.t); });
+      std::vector<Cand> keep;
+      auto have_cfg = [&](int c) { for (auto& k : keep) if (k.c == c) return true; return false; };
+      for (auto& cd : all) {
+        int bn, st_, cg; b200_hgemm_config_info(cd.c, &bn, &st_, &cg);
+        // the six fastest, plus the fastest schedule of every CTA-pair configuration within 8 % of the best
+        if (keep.size() < 6 || (cg == 2 && !have_cfg(cd.c) && median(cd.t) <= 1.08f * median(all[0].t))) keep.push_back(cd);
+      }
+      all.swap(keep);
+      for (auto& cd : all) cd.t.clear();
+      for (int r = 0; r < iters + 1; ++r) {
+        // three library calls per round keep the mix (and the power state) close to the harness's rotation
+        for (int rep = 0; rep < 3; ++rep) { const float tb = once_wall([&] { cublas_tn(p, p.Cref); }); if (r) blas_t.push_back(tb); }
+        for (auto& cd : all) { const float t = once_wall([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
+      }
+    } else {
+      for (int r = 0; r < iters + 1; ++r) {
+        const float tb = once_event([&] { cublas_tn(p, p.Cref); });
+        if (r) blas_t.push_back(tb);
+        for (auto& cd : all) { const float t = once_event([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
+      }
     }
     cudaEventDestroy(ea); cudaEventDestroy(eb);
     // event metric: median time; wall metric: the time whose rate is the mean rate (the harness averages TFLOP/s)
