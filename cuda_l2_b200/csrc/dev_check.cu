@@ -305,7 +305,9 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     for (int c = 0; c < ncfg; ++c) {
       int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
       if ((p.M + 127) / 128 < cg * cm || (p.N + bn - 1) / bn < cn) continue;   // part of the cluster would only see padding
-      if (cg == 2 && cm * cn > 1) continue;   // pair + multicast: exact, but slower than plain pairs in every harness-metric run
+      // pair + multicast: exact, but slower than plain pairs in every event-time run; the wall-metric mode keeps them,
+      // because they move the fewest bytes per FLOP (what cuBLAS's 2x2_2cta kernels do) and that is what counts at the power cap
+      if (cg == 2 && cm * cn > 1 && !wall_metric) continue;
       const bool plain = (cm * cn == 1) && bn >= 64;
       const int nm = (p.M + 128 * cg * cm - 1) / (128 * cg * cm);
       const int nn = (p.N + bn * cn - 1) / (bn * cn);
