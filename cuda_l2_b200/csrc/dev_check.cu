@@ -2,6 +2,7 @@
 //
 //   dev_check check <acc_bits> <cfg|-1> <M> <N> <K> [gm splits]   exactness vs an independent GPU checker
 //   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters]  CUDA-event timing (+ cuBLAS for scale)
+//   dev_check sustain <acc_bits> <cfg|-1> <M> <N> <K> [seconds gm splits]   burst vs power-capped throughput, ours and cuBLAS
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
 //   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
@@ -28,6 +29,7 @@
 #include "../../include/b200_hgemm.h"
 #include <chrono>
 #include <random>
+#include <thread>
 
 #define CK(x)                                                                              \
   do {                                                                                     \
@@ -240,6 +242,45 @@ static int do_time(int acc, int cfg, int M, int N, int K, int iters) {
          acc, cfg, sel, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
   p.release();
   fflush(stdout);
+  return 0;
+}
+
+// sustain: back-to-back launches of one kernel for `seconds`, throughput per ~50 ms window. The first windows run at
+// burst clocks, the last ones at whatever the power cap leaves: the gap between a kernel's two figures is its power
+// appetite, and the harness (seven efficient kernels in rotation, seconds per shape) lives in the second state.
+// Run nvidia-smi -lms alongside (tools/gpu/*.sh) to see clocks and watts for each phase.
+static int do_sustain(int acc, int cfg, int M, int N, int K, double seconds, int gm, int splits) {
+  Problem p; alloc_random(p, M, N, K);
+  const double flops = 2.0 * M * N * K;
+  if (run_ours(acc, cfg, p, gm, splits) || cudaDeviceSynchronize() != cudaSuccess) { printf("SUSTAIN launch fail\n"); return 1; }
+  struct Fn { const char* name; std::function<void()> f; };
+  std::vector<Fn> fns = {{"ours", [&] { run_ours(acc, cfg, p, gm, splits); }}, {"cublas", [&] { cublas_tn(p, p.Cref); }}};
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (auto& fn : fns) {
+    // idle first, so that every kernel starts from the same cool state
+    CK(cudaDeviceSynchronize());
+    std::this_thread::sleep_for(std::chrono::milliseconds(1500));
+    float one = time_ms(fn.f, 3, 1);
+    const int per_window = std::max(1, int(50.0 / std::max(one, 1e-3f)));
+    std::vector<double> tf;
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::duration<double>(seconds);
+    while (std::chrono::steady_clock::now() < t_end) {
+      CK(cudaEventRecord(a));
+      for (int i = 0; i < per_window; ++i) fn.f();
+      CK(cudaEventRecord(b));
+      CK(cudaEventSynchronize(b));
+      float ms; CK(cudaEventElapsedTime(&ms, a, b));
+      tf.push_back(flops * per_window / ms * 1e-9);
+    }
+    const size_t n = tf.size(), tail = std::max<size_t>(1, n / 4);
+    double first = tf[0], last = 0;
+    for (size_t i = n - tail; i < n; ++i) last += tf[i] / tail;
+    printf("SUSTAIN acc=%d %s cfg=%d gm=%d splits=%d %dx%dx%d  windows=%zu x %d launches  first %.1f TFLOP/s  last-quarter %.1f TFLOP/s  (%.3f)\n",
+           acc, fn.name, cfg, gm, splits, M, N, K, n, per_window, first, last, last / first);
+    fflush(stdout);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  p.release();
   return 0;
 }
 
@@ -585,6 +626,9 @@ int main(int argc, char** argv) {
                     argc > 8 ? atoi(argv[8]) : 1);
   if (mode == "time" && argc >= 7)
     return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20);
+  if (mode == "sustain" && argc >= 7)
+    return do_sustain(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atof(argv[7]) : 3.0,
+                      argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 1);
   if (mode == "sweep" && argc >= 6)
     return do_sweep(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 20);
 #ifdef B200_HGEMM_TRACE
