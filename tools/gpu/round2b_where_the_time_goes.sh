@@ -38,7 +38,7 @@ echo "== 3. ncu (serialised, cold: compare shapes of the numbers)" >> $LOG
 M="gpu__time_duration.sum,sm__cycles_elapsed.avg.per_second,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__data_bank_conflicts_pipe_lsu.sum,smsp__inst_executed.sum,launch__grid_size,launch__cluster_size"
 for spec in "-1 4096 4096 4096" "-1 512 8192 8192" "-1 128 8192 16384" "-1 8192 8192 8192"; do
   set -- $spec
-  timeout 300 ncu --metrics $M --clock-control none -s 4 -c 8 --csv --log-file gpurun_out/round2b_ncu_$2x$3x$4.csv \
+  timeout 300 ncu --metrics $M --clock-control none -s 4 -c 16 --csv --log-file gpurun_out/round2b_ncu_$2x$3x$4.csv \
       $DC time 32 $1 $2 $3 $4 2 >> $LOG 2>&1
 done
 grep -E "SUSTAIN|TRACE|median|exit" $LOG | cut -c1-220 | tail -120
