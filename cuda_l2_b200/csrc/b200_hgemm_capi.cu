@@ -30,6 +30,29 @@ int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int
   return st;
 }
 
+template <class Cfg>
+int schedule_units(int M, int N, int K, int splits, int num_sms, int worker, int* units, int max_units,
+                   int* num_workers, int* sk_tiles, int* contributors) {
+  using namespace b200;
+  const host::Plan p = host::make_plan<Cfg>(M, N, K, num_sms / Cfg::CLUSTER_CTAS, splits);
+  if (num_workers) *num_workers = p.workers;
+  if (sk_tiles) *sk_tiles = p.sk_tiles;
+  if (worker < 0 || worker >= p.workers) return host::kBadShape;
+  WorkIter it(worker, p.workers, p.num_tiles, p.nkb, p.splits, p.sk_tiles);
+  WorkUnit u;
+  int n = 0;
+  while (it.next(u)) {
+    if (n < max_units && units) {
+      units[3 * n] = u.tile; units[3 * n + 1] = u.kb0; units[3 * n + 2] = u.kb1;
+      if (contributors)
+        contributors[n] = (p.sk_tiles && u.kb0 == 0 && u.kb1 < p.nkb)
+                              ? streamk_contributors(worker, p.workers, p.sk_tiles * p.nkb, u.tile, p.nkb) : 0;
+    }
+    ++n;
+  }
+  return n;
+}
+
 int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m,
         int max_ctas, int splits, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -66,6 +89,21 @@ int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n) {
     if (cluster_m) *cluster_m = CM;           \
     if (cluster_n) *cluster_n = CN;           \
     return 0;
+    B200_HGEMM_CONFIGS(B200_CASE)
+#undef B200_CASE
+    default:
+      return b200::host::kBadConfig;
+  }
+}
+
+int b200_hgemm_schedule_units(int config_id, int M, int N, int K, int splits, int num_sms, int worker, int* units,
+                              int max_units, int* num_workers, int* sk_tiles, int* contributors) {
+  if (M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return b200::host::kBadShape;
+  switch (config_id) {
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN)                                                                   \
+  case ID:                                                                                                      \
+    return schedule_units<b200::Config<BN, STAGES, CG, true, CM, CN>>(M, N, K, splits, num_sms, worker, units, \
+                                                                      max_units, num_workers, sk_tiles, contributors);
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
     default:

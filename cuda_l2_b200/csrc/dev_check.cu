@@ -1,7 +1,8 @@
 // dev_check — standalone bring-up / tuning tool for libb200_hgemm.so (developer tool, not product).
 //
 //   dev_check check <acc_bits> <cfg|-1> <M> <N> <K> [gm splits]   exactness vs an independent GPU checker
-//   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters]  CUDA-event timing (+ cuBLAS for scale)
+//                                                     (splits: 1 none, >1 workspace, -2/-4/-8 cluster, 100/101 stream-K)
+//   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters gm splits]  CUDA-event timing (+ cuBLAS for scale)
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
 //   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
@@ -141,7 +142,7 @@ static int do_check(int acc, int cfg, int M, int N, int K, int gm = 0, int split
   p.reset_c();
   CK(cudaDeviceSynchronize());
   int st = run_ours(acc, cfg, p, gm, splits);
-  if (splits > 1 && st == 0) st = run_ours(acc, cfg, p, gm, splits);   // twice: the counters must reset themselves
+  if (splits != 1 && st == 0) st = run_ours(acc, cfg, p, gm, splits);   // twice: the counters / flags must reset themselves
   cudaError_t e = cudaDeviceSynchronize();
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
   if (st != 0 || e != cudaSuccess) {
@@ -225,17 +226,17 @@ static void alloc_random(Problem& p, int M, int N, int K) {
   CK(cudaDeviceSynchronize());
 }
 
-static int do_time(int acc, int cfg, int M, int N, int K, int iters) {
+static int do_time(int acc, int cfg, int M, int N, int K, int iters, int gm = 0, int splits = 1) {
   Problem p; alloc_random(p, M, N, K);
   const double flops = 2.0 * M * N * K;
-  int st = run_ours(acc, cfg, p);
+  int st = run_ours(acc, cfg, p, gm, splits);
   cudaError_t e = cudaDeviceSynchronize();
   if (st != 0 || e != cudaSuccess) { printf("TIME launch fail %d %s\n", st, cudaGetErrorString(e)); return 1; }
-  float ours = time_ms([&] { run_ours(acc, cfg, p); }, iters);
+  float ours = time_ms([&] { run_ours(acc, cfg, p, gm, splits); }, iters);
   float blas = time_ms([&] { cublas_tn(p, p.Cref); }, iters);
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
-  printf("TIME acc=%d cfg=%d(%d) %dx%dx%d  ours %.2f us %.1f TFLOP/s | cublas(fp32acc) %.2f us %.1f TFLOP/s | ratio %.3f\n",
-         acc, cfg, sel, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
+  printf("TIME acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ours %.2f us %.1f TFLOP/s | cublas(fp32acc) %.2f us %.1f TFLOP/s | ratio %.3f\n",
+         acc, cfg, sel, gm, splits, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
   p.release();
   fflush(stdout);
   return 0;
@@ -315,6 +316,17 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
       if (plain && cg == 1 && nkb >= 8 && nm * nn <= 148)
         for (int cs : {2, 4, 8})
           if (nm * nn * cs <= 296 && nkb >= 2 * cs) cands.push_back({0, -cs});   // cluster (DSMEM) split-K
+      // stream-K (splits code 100: the partial last wave, 101: that plus one full wave) where the tile count leaves
+      // more than 5 % of the last wave empty
+      const int workers = 148 / cg;
+      if (plain && (nm * nn) % workers != 0 && nkb >= 8 &&
+          double(nm * nn) / (double((nm * nn + workers - 1) / workers) * workers) < 0.95) {
+        const std::vector<int> sk_gms = (nm * nn > workers && nm > 1 && nn > 1) ? std::vector<int>{4, 16} : std::vector<int>{0};
+        for (int g : sk_gms) {
+          cands.push_back({g, 100});
+          if (nm * nn > workers) cands.push_back({g, 101});
+        }
+      }
       for (const auto& cand_ : cands) {
         const int gm = cand_.first, sp = cand_.second;
         if (gm > 1 && gm / 2 >= nm) continue;
@@ -470,7 +482,8 @@ int main(int argc, char** argv) {
     return do_check(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 0,
                     argc > 8 ? atoi(argv[8]) : 1);
   if (mode == "time" && argc >= 7)
-    return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20);
+    return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20,
+                   argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 1);
   if (mode == "sweep" && argc >= 6)
     return do_sweep(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 20);
   if (mode == "probe") { probe_cluster_addresses<<<4, 32>>>(); CK(cudaDeviceSynchronize()); return 0; }

@@ -142,7 +142,9 @@ inline int validate(const void* A, const void* Bt, const void* C, int M, int N, 
 struct SplitKScratch {
   int dev = -1; cudaStream_t stream = nullptr; float* ws = nullptr; unsigned* ctr = nullptr;
 };
-constexpr size_t kSplitKWsBytes = size_t(160) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
+constexpr size_t kSplitKWsBytes = size_t(kMaxStreamKSlots) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
+// split-K arrive/done counters, then one stream-K flag per (CTA slot, epilogue warp)
+constexpr size_t kSplitKCtrBytes = (2 * kMaxSplitTiles + kMaxStreamKSlots * kStreamKFlagsPerSlot) * sizeof(unsigned);
 inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
   static thread_local SplitKScratch pool[8];
   SplitKScratch* free_slot = nullptr;
@@ -153,9 +155,9 @@ inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
   if (!free_slot) return kBadConfig;
   cudaError_t err = cudaMalloc(&free_slot->ws, kSplitKWsBytes);
   if (err != cudaSuccess) return int(err);
-  err = cudaMalloc(&free_slot->ctr, 2 * kMaxSplitTiles * sizeof(unsigned));
+  err = cudaMalloc(&free_slot->ctr, kSplitKCtrBytes);
   if (err != cudaSuccess) { cudaFree(free_slot->ws); free_slot->ws = nullptr; return int(err); }
-  err = cudaMemsetAsync(free_slot->ctr, 0, 2 * kMaxSplitTiles * sizeof(unsigned), stream);
+  err = cudaMemsetAsync(free_slot->ctr, 0, kSplitKCtrBytes, stream);
   if (err != cudaSuccess) return int(err);
   free_slot->dev = dev; free_slot->stream = stream;
   *out = free_slot;
@@ -174,6 +176,59 @@ int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   while (splits > 1 && (splits - 1) * ((nkb + splits - 1) / splits) >= nkb) --splits;   // no empty split
   while (splits > 1 && size_t(tiles) * splits * kBlockM * Cfg::BN * sizeof(float) > kSplitKWsBytes) --splits;
   return std::max(splits, 1);
+}
+
+// `splits` values with a special meaning (besides > 1: workspace split-K, -2/-4/-8: cluster split-K)
+constexpr int kStreamKTail = 100;           // stream-K over the tiles of the partial last wave
+constexpr int kStreamKTailPlusWave = 101;   // ... plus one full wave, so that every worker's slice is longer than a tile
+constexpr int kMinStreamKSlice = 4;         // k-blocks; shorter slices are all pipeline fill and fix-up
+
+// What a launch will run: how many workers (CTAs, CTA pairs or clusters), which K-decomposition.
+struct Plan {
+  int num_tiles, nkb;
+  int workers;          // grid = workers * (CTAs per worker)
+  int splits;           // > 1: split-K, one worker per (tile, split)
+  int cluster_reduce;   // != 0: the splits of a tile form a cluster of this many CTAs and reduce through DSMEM
+  int sk_tiles;         // > 0: stream-K over the first sk_tiles tiles
+};
+
+// `workers_avail`: workers the device can hold at once (SMs / CTAs per worker, after max_ctas and cluster occupancy).
+template <class Cfg>
+Plan make_plan(int M, int N, int K, int workers_avail, int splits) {
+  Plan p{};
+  const int num_m_blocks = (M + Cfg::TILE_M * Cfg::CLUSTER_M - 1) / (Cfg::TILE_M * Cfg::CLUSTER_M);
+  const int num_n_blocks = (N + Cfg::BN * Cfg::CLUSTER_N - 1) / (Cfg::BN * Cfg::CLUSTER_N);
+  p.num_tiles = num_m_blocks * num_n_blocks;
+  p.nkb = (K + kBlockK - 1) / kBlockK;
+  p.workers = std::max(workers_avail, 1);
+  const bool plain = Cfg::MCAST_CTAS == 1 && Cfg::BN >= 64;   // the K-decompositions are wired for these
+  int sk_mode = 0;
+  if (splits == kStreamKTail || splits == kStreamKTailPlusWave) { sk_mode = splits; splits = 1; }
+  if (!plain) splits = 1;
+  if (splits < -1) {
+    int cs = -splits;
+    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8)) {
+      // every CTA of the cluster must own at least one k-block: halve the cluster until no k-range is empty
+      while (cs > 1 && (cs - 1) * ((p.nkb + cs - 1) / cs) >= p.nkb) cs /= 2;
+      if (cs > 1) p.cluster_reduce = cs;
+    }
+    splits = 1;
+  }
+  p.splits = clamp_splits<Cfg>(splits, M, N, K, p.workers);
+  if (p.cluster_reduce) {
+    p.workers = p.num_tiles * p.cluster_reduce;   // one cluster per tile, one CTA per k-range
+    p.splits = p.cluster_reduce;
+  } else if (p.splits > 1) {
+    p.workers = p.num_tiles * p.splits;           // exactly one CTA per (tile, split) unit
+  } else {
+    if (sk_mode && plain && p.num_tiles % p.workers != 0 && p.workers * Cfg::CTA_GROUP <= kMaxStreamKSlots) {
+      int sk = p.num_tiles % p.workers;
+      if (sk_mode == kStreamKTailPlusWave && p.num_tiles > p.workers) sk += p.workers;
+      if (sk * p.nkb / p.workers >= kMinStreamKSlice) p.sk_tiles = sk;
+    }
+    if (!p.sk_tiles && p.workers > p.num_tiles) p.workers = p.num_tiles;
+  }
+  return p;
 }
 
 inline bool cache_hints_enabled() {
@@ -211,10 +266,6 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &mb)) != kOk) return st;
   if ((st = cache.get(C, M, N, 32, &mc, Cfg::EPI_N)) != kOk) return st;
 
-  // schedule granularity: cluster blocks of (CLUSTER_M x TILE_M) x (CLUSTER_N x BN); 1 x 1 for plain configs
-  const int num_m_blocks = (M + Cfg::TILE_M * Cfg::CLUSTER_M - 1) / (Cfg::TILE_M * Cfg::CLUSTER_M);
-  const int num_n_blocks = (N + Cfg::BN * Cfg::CLUSTER_N - 1) / (Cfg::BN * Cfg::CLUSTER_N);
-  const int num_tiles = num_m_blocks * num_n_blocks;
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CLUSTER_CTAS;
   if constexpr (Cfg::CLUSTER_CTAS > 2) {
     // clusters must fit inside a GPC: ask the runtime how many can be resident at once (cached per device)
@@ -237,43 +288,23 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     }
     if (max_ctas <= 0 || workers > max_clusters) workers = std::min(workers, max_clusters);
   }
-  if (workers < 1) workers = 1;
-  if (Cfg::MCAST_CTAS > 1 || Cfg::BN < 64) splits = 1;   // split-K is wired for plain configs with BN >= 64
-  // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
-  int cluster_reduce = 0;
-  if (splits < -1) {
-    int cs = -splits;
-    const int nkb = (K + kBlockK - 1) / kBlockK;
-    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8)) {
-      // every CTA of the cluster must own at least one k-block: halve the cluster until no k-range is empty
-      while (cs > 1 && (cs - 1) * ((nkb + cs - 1) / cs) >= nkb) cs /= 2;
-      if (cs > 1) cluster_reduce = cs;
-    }
-    splits = 1;
-  }
-  splits = clamp_splits<Cfg>(splits, M, N, K, workers);
+  Plan plan = make_plan<Cfg>(M, N, K, workers, splits);
   float* ws = nullptr;
   unsigned* ctr = nullptr;
-  if (cluster_reduce) {
-    workers = num_tiles * cluster_reduce;   // one cluster per tile, one CTA per k-range
-    splits = cluster_reduce;
-  } else if (splits > 1) {
+  if ((plan.splits > 1 && !plan.cluster_reduce) || plan.sk_tiles) {
     SplitKScratch* sk = nullptr;
     if (splitk_scratch(di.dev, stream, &sk) == kOk) {
       ws = sk->ws; ctr = sk->ctr;
-      workers = num_tiles * splits;        // exactly one CTA per (tile, split) unit
     } else {
       cudaGetLastError();
-      splits = 1;                          // no scratch (allocation failed / more than 8 streams): run unsplit
-      if (workers > num_tiles) workers = num_tiles;
+      plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed / more than 8 streams): run undivided
     }
-  } else if (workers > num_tiles) {
-    workers = num_tiles;
   }
+  const int cluster_reduce = plan.cluster_reduce;
   if (group_m <= 0) group_m = (Cfg::CTA_GROUP == 2) ? 8 : 16;
 
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(workers * (cluster_reduce || splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
+  cfg.gridDim = dim3(unsigned(plan.workers * (cluster_reduce || plan.splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
   cfg.blockDim = dim3(kNumThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -294,7 +325,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { hint_a = ptx::kL2EvictFirst; hint_b = ptx::kL2EvictLast; }
     else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { hint_b = ptx::kL2EvictFirst; hint_a = ptx::kL2EvictLast; }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, cluster_reduce ? 1 : 0, ws, ctr,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, plan.splits, cluster_reduce ? 1 : 0, plan.sk_tiles, ws, ctr,
                                      static_cast<__half*>(C), hint_a, hint_b);
   return e == cudaSuccess ? kOk : int(e);
 }

@@ -26,12 +26,16 @@
 //     a tcgen05.commit multicast to every CTA of the consumer's cluster row and column;
 //   * split-K for problems with few output tiles and long K, two flavours, both deterministic: partial tiles
 //     through an fp32 global workspace with a distributed reduction (up to 32 splits), or the splits of a tile
-//     form a cluster and reduce through distributed shared memory (2/4/8 splits, no workspace).
+//     form a cluster and reduce through distributed shared memory (2/4/8 splits, no workspace);
+//   * stream-K for tile counts that leave the last wave partly empty: the first tiles of the schedule are cut along
+//     K into one equal slice per worker (hgemm_schedule.cuh), the partial sums of a tile meet in its owner's
+//     epilogue through the same workspace, in fixed k order.
 #pragma once
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "hgemm_schedule.cuh"
 #include "ptx_sm100.cuh"
 
 
@@ -104,25 +108,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;   // SWIZZLE_128B
   return d;
 }
-
-struct TileCoord { int m_blk, n_blk; };
-
-// Grouped rasterisation: walk `group_m` row-blocks down before stepping one column-block right,
-// so a wave of CTAs shares a compact set of A/B panels in L2.
-__device__ __forceinline__ TileCoord tile_coord(int t, int num_m_blocks, int num_n_blocks, int group_m) {
-  const int tiles_per_group = group_m * num_n_blocks;
-  const int group = t / tiles_per_group;
-  const int first_m = group * group_m;
-  const int gsz = min(group_m, num_m_blocks - first_m);
-  const int in_group = t - group * tiles_per_group;
-  TileCoord c;
-  c.m_blk = first_m + in_group % gsz;
-  c.n_blk = in_group / gsz;
-  // serpentine: odd groups sweep N backwards, so the B panels touched last by one group are still in L2 for the next
-  if (group & 1) c.n_blk = num_n_blocks - 1 - c.n_blk;
-  return c;
-}
-
 
 constexpr int kMaxSplitTiles = 256;   // split-K is only used when tiles * splits <= #SMs
 
@@ -293,6 +278,165 @@ __device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int spli
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stream-K (hgemm_schedule.cuh). Partial tiles travel through the global workspace as REGISTER IMAGES: an epilogue
+// warp holds 32 rows x 64 accumulator columns of a chunk, one row per lane; the lanes write register quad i of the
+// chunk to 32 consecutive uint4 and the owner's same warp reads them back the same way, so both directions are
+// fully coalesced and no thread ever needs another thread's element. One flag per (CTA slot, epilogue warp):
+// raised by the contributor warp after its chunks are written, polled and lowered again by the owner warp, so the
+// warps stay as decoupled as in the plain epilogue and the flags are zero again when the grid ends.
+constexpr int kMaxStreamKSlots = 160;   // CTAs of a launch (>= 148 SMs), one partial-tile slot each
+constexpr int kStreamKFlagsPerSlot = 8; // epilogue warps
+
+template <class Cfg>
+struct StreamK {
+  static constexpr int REGS = Cfg::ACC_F32 ? Cfg::EPI_N : Cfg::EPI_N / 2;   // 32-bit registers per lane per chunk
+  static constexpr int R4 = REGS / 4;
+  static constexpr int CHUNK_U4 = R4 * 32;                                  // one warp, one chunk
+  static constexpr int SLOT_U4 = 4 * Cfg::EPI_CHUNKS * CHUNK_U4;            // one CTA: 128 rows x BN columns
+  static constexpr size_t SLOT_BYTES = size_t(SLOT_U4) * 16;
+};
+
+// this warp's chunk `j` of the accumulator, raw: fp32 bit patterns, or fp16 pairs (two columns per register)
+template <class Cfg>
+__device__ __forceinline__ void streamk_load_chunk(uint32_t taddr, uint32_t (&r)[StreamK<Cfg>::REGS]) {
+  using namespace ptx;
+  static_assert(Cfg::EPI_N == 64, "stream-K is wired for 64-column epilogue chunks");
+  if constexpr (Cfg::ACC_F32) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32b_x32(taddr, v0);
+    tmem_ld_32x32b_x32(taddr + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { r[i] = v0[i]; r[32 + i] = v1[i]; }
+  } else {
+    tmem_ld_32x32b_x32_pack16(taddr, r);
+    tmem_ld_wait();
+  }
+}
+
+// registers -> swizzled staging buffer -> TMA store of one 32 x EPI_N chunk (shared by the plain and the owner epilogue)
+template <class Cfg>
+__device__ __forceinline__ void epilogue_store_chunk(const uint32_t (&packed)[Cfg::EPI_N / 2], uint32_t epi_buf,
+                                                     uint32_t row_off, uint32_t sw, int lane,
+                                                     const CUtensorMap* tmap_c, int nc, int m0, int M, int N) {
+  using namespace ptx;
+  // the previous store from this warp's staging buffer must have finished reading it
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  const uint32_t dst = epi_buf + row_off;
+#pragma unroll
+  for (int c = 0; c < Cfg::EPI_N / 8; ++c)
+    st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
+      tma_store_2d(tmap_c, epi_buf, nc, m0);
+    tma_store_commit();
+  }
+}
+
+struct EpilogueWarp {          // what one epilogue warp knows about itself
+  int q, ew, lane;             // TMEM lane quadrant, index among the epilogue warps (0..7), lane
+  int j_begin, j_end;          // its share of a tile's column chunks
+  uint32_t epi_buf, row_off, sw;
+};
+
+// Contributor: spill this warp's chunks of the partial accumulator to the CTA's slot and raise the warp's flag.
+// `release_tmem` hands the accumulator stage back to the MMA warp as soon as the last chunk is in registers.
+template <class Cfg, class ReleaseTmem>
+__device__ __forceinline__ void streamk_contribute(const EpilogueWarp& w, uint32_t taddr0, uint4* __restrict__ ws,
+                                                   unsigned* __restrict__ flags, int slot, ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  uint4* base = ws + size_t(slot) * SK::SLOT_U4 + size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    uint32_t r[SK::REGS];
+    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+    if (j == w.j_end - 1) release_tmem();
+    uint4* dst = base + size_t(j) * SK::CHUNK_U4;
+#pragma unroll
+    for (int i = 0; i < SK::R4; ++i) st_global_cg_v4(dst + i * 32, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  }
+  __threadfence();   // every lane's stores are visible at gpu scope before lane 0 publishes the flag
+  __syncwarp();
+  if (w.lane == 0) st_release_gpu(flags + slot * kStreamKFlagsPerSlot + w.ew, 1u);
+}
+
+// Owner: accumulator + the partials of `n` contributors (slots slot0, slot0 + slot_stride, ... — increasing k),
+// summed in fp32 in that fixed order, rounded once, stored like any other tile.
+template <class Cfg, class ReleaseTmem>
+__device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t taddr0, const uint4* __restrict__ ws,
+                                            unsigned* __restrict__ flags, int slot0, int slot_stride, int n,
+                                            const CUtensorMap* tmap_c, int m0, int n0, int M, int N,
+                                            ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  if (w.lane == 0) {
+    for (int p = 0; p < n; ++p) {
+      const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(f) == 0u) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { printf("b200_hgemm watchdog: stream-K slot %d never arrived\n", slot0 + p * slot_stride); __trap(); }
+      }
+    }
+  }
+  __syncwarp();
+  const size_t warp_off = size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    uint32_t r[SK::REGS];
+    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+    if (j == w.j_end - 1) release_tmem();
+    float f[Cfg::EPI_N];
+    if constexpr (Cfg::ACC_F32) {
+#pragma unroll
+      for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = __uint_as_float(r[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&r[i]);
+        f[2 * i] = __low2float(h);
+        f[2 * i + 1] = __high2float(h);
+      }
+    }
+    for (int p = 0; p < n; ++p) {
+      const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 + warp_off + size_t(j) * SK::CHUNK_U4;
+      // in batches of four quads, so that at most 16 loaded registers are in flight next to the 64 sums
+#pragma unroll
+      for (int b = 0; b < SK::R4 / 4; ++b) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = ld_global_cg_v4(src + (4 * b + i) * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if constexpr (Cfg::ACC_F32) {
+              f[4 * (4 * b + i) + c] += __uint_as_float(x[c]);
+            } else {
+              const __half2 h = *reinterpret_cast<const __half2*>(&x[c]);
+              f[8 * (4 * b + i) + 2 * c] += __low2float(h);
+              f[8 * (4 * b + i) + 2 * c + 1] += __high2float(h);
+            }
+          }
+        }
+        __syncwarp();   // keeps the compiler from hoisting the next batch's loads above these sums
+      }
+    }
+    uint32_t packed[Cfg::EPI_N / 2];
+#pragma unroll
+    for (int i = 0; i < Cfg::EPI_N / 2; ++i) packed[i] = pack_f16x2_rn(f[2 * i], f[2 * i + 1]);
+    epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
+  }
+  // lower the flags again: this warp is their only reader, and the next writer is a later launch
+  __syncwarp();
+  if (w.lane == 0)
+    for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kNumThreads, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
@@ -301,8 +445,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
                 int M, int N, int K, int group_m,
                 int splits,                       // split-K factor; > 1 only with CLUSTER_CTAS == 1, one unit per CTA
                 int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
-                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K)
-                unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
+                int sk_tiles,                     // stream-K: the first sk_tiles tiles are cut along K across all workers (0 = off)
+                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K) / stream-K slots
+                unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] split-K arrive / done counters, then the
+                                                     // stream-K flags; all zero between launches
                 __half* __restrict__ c_raw,       // C base pointer, used by the split-K reductions' direct stores
                 uint64_t hint_a, uint64_t hint_b  /* L2 eviction priority of the A / B loads (ptx::kL2Evict*) */) {
   constexpr int BN = Cfg::BN;
@@ -345,10 +491,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
   const int num_workers = gridDim.x / Cfg::CLUSTER_CTAS;   // clusters (or single CTAs)
   const int worker = blockIdx.x / Cfg::CLUSTER_CTAS;
-  // A work unit is (tile, k-split). splits == 1: units == tiles, walked persistently. splits > 1: the host
-  // launches exactly one CTA per unit, so the sibling splits of a tile run concurrently.
-  const int num_units = num_tiles * splits;
-  const int kb_per_split = (num_k_blocks + splits - 1) / splits;
+  // A work unit is (tile, k-block range), see hgemm_schedule.cuh. splits == 1: whole tiles walked persistently
+  // (after the worker's stream-K slice, if any). splits > 1: the host launches exactly one CTA per (tile, split)
+  // unit, so the sibling splits of a tile run concurrently.
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && elect_one()) {
@@ -397,14 +542,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const uint32_t a_slice = uint32_t(cn) * (Cfg::A_BOX_ROWS * kBlockK * 2);
     const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
     int stage = 0; uint32_t phase = 0;
-    for (int u = worker; u < num_units; u += num_workers) {
-      const int t = u / splits;
-      const int kb0 = (u - t * splits) * kb_per_split;
-      const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
-      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
+    WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+    WorkUnit u;
+    while (work.next(u)) {
+      const TileCoord tc = tile_coord(u.tile, num_m_blocks, num_n_blocks, group_m);
       const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM + cn * Cfg::A_BOX_ROWS;
       const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
@@ -439,9 +583,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int u = worker; u < num_units; u += num_workers) {
-        const int kb0 = (u % splits) * kb_per_split;
-        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
+      WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+      WorkUnit u;
+      while (work.next(u)) {
+        const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -485,9 +630,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const int j_end = min(Cfg::EPI_CHUNKS, j_begin + CPG);
     const bool working = eg < Cfg::EPI_GROUPS;      // narrow tiles keep the second set of warps idle
     int acc = 0; uint32_t acc_phase = 0;
+    const EpilogueWarp ew{q, warp - kEpiWarp0, lane, j_begin, j_end, epi_buf, row_off, sw};
     if (working) {
-    for (int u = worker; u < num_units; u += num_workers) {
-      const int t = u / splits;
+    WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+    WorkUnit u;
+    while (work.next(u)) {
+      const int t = u.tile;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
       const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
       const int m0 = m_tile0 + q * 32;
@@ -501,13 +649,37 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
         if (splits > 1 && cluster_reduce) {
           cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
-          ck_m_base = m_tile0; ck_n0 = n0; ck_split = u - t * splits;
+          ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;
           continue;   // the reduction runs after the cluster barrier below
         }
         if (splits > 1) {
-          splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, m_tile0, n0, M, N,
+          splitk_epilogue<Cfg>(taddr0, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
                                splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
+        }
+      }
+      // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
+      auto release_tmem = [&] {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
+          else mbar_arrive(tmem_empty0 + 8 * acc);
+        }
+      };
+      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64) {
+        if (u.kb0 > 0 || u.kb1 < num_k_blocks) {   // stream-K: a partial sum of the tile (never taken when sk_tiles == 0)
+          uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
+          unsigned* flags = splitk_ctr + 2 * kMaxSplitTiles;
+          if (u.kb0 > 0) {
+            streamk_contribute<Cfg>(ew, taddr0, ws4, flags, worker * CG + int(cta_rank), release_tmem);
+          } else {
+            const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
+            streamk_own<Cfg>(ew, taddr0, ws4, flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m0, n0, M, N,
+                             release_tmem);
+          }
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          continue;
         }
       }
       for (int j = j_begin; j < j_end; ++j) {
@@ -533,31 +705,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == j_end - 1) {
-          // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
-            else mbar_arrive(tmem_empty0 + 8 * acc);
-          }
-        }
-        // the previous store from this warp's staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        const uint32_t dst = epi_buf + row_off;
-#pragma unroll
-        for (int c = 0; c < EN / 8; ++c)
-          st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1],
-                       packed[4 * c + 2], packed[4 * c + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const int nc = n0 + j * EN;
-          if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
-            tma_store_2d(&tmap_c, epi_buf, nc, m0);
-          tma_store_commit();
-        }
+        if (j == j_end - 1) release_tmem();
+        epilogue_store_chunk<Cfg>(packed, epi_buf, row_off, sw, lane, &tmap_c, n0 + j * EN, m0, M, N);
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }

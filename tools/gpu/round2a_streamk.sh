@@ -1,0 +1,54 @@
+#!/bin/bash
+# Round 2, first GPU call: validate the stream-K branch (never run on a GPU before this script).
+#   1. regression ladder of the plain schedule (the loops were rewritten around WorkIter);
+#   2. stream-K exactness: every plain config x {tail, tail+wave} x shapes with 1..13 contributors per tile;
+#   3. A/B timings on the wave-quantised shapes that motivated it (tile count = 0.865 of a wave multiple);
+#   4. the GPU test-suite.
+# One process per case so that a trap in one configuration cannot poison the rest.
+cd "$(dirname "$0")/../.." || exit 1
+mkdir -p gpurun_out
+LOG=gpurun_out/round2a.log
+: > $LOG
+DC=cuda_l2_b200/lib/dev_check
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
+run() { timeout 120 $DC "$@" >> $LOG 2>&1; rc=$?; [ $rc -ne 0 ] && echo "  -> exit $rc : $*" >> $LOG; }
+echo "== 1. plain regression" >> $LOG
+for acc in 32 16; do
+  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20; do
+    run check $acc $cfg 1024 1536 1024
+    run check $acc $cfg 1000 1000 1000
+  done
+  run check $acc -1 4096 4096 4096
+  run check $acc -1 64 64 16384
+  run check $acc 1 256 512 2048 0 8
+  run check $acc 1 256 512 2048 0 -4
+done
+echo "== 2. stream-K exactness" >> $LOG
+for acc in 32 16; do
+  for cfg in 0 1 2 3 4 5 6; do
+    for sk in 100 101; do
+      run check $acc $cfg 512 768 4096 0 $sk
+      run check $acc $cfg 1000 1224 2048 0 $sk
+      run check $acc $cfg 512 8192 8192 0 $sk
+      run check $acc $cfg 4096 4096 4096 8 $sk
+    done
+  done
+done
+grep -c PASS $LOG >> $LOG; grep -c "FAIL\|exit" $LOG >> $LOG
+echo "== 3. A/B timings (same process order: plain, tail, tail+wave)" >> $LOG
+ab() { for sk in 1 100 101; do run time "$1" "$2" "$3" "$4" "$5" 30 "$6" $sk; done; }
+ab 32 3 512 8192 8192 0
+ab 32 3 1024 4096 8192 0
+ab 32 4 512 4096 8192 0
+ab 32 3 1024 8192 8192 0
+ab 32 6 4096 4096 4096 8
+ab 32 3 4096 4096 4096 8
+ab 32 3 2048 11008 4096 8
+ab 32 4 12288 2048 4096 8
+ab 32 0 1024 1024 4096 0
+ab 32 4 1024 1024 4096 0
+ab 16 3 512 8192 8192 0
+ab 16 3 4096 4096 4096 8
+echo "== 4. pytest" >> $LOG
+timeout 1200 python -m pytest tests -m gpu -x -q >> $LOG 2>&1; echo "pytest rc=$?" >> $LOG
+grep -E "FAIL|exit|watchdog|TIME|pytest rc|passed|failed" $LOG | tail -60
