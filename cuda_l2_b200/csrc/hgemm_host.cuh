@@ -236,6 +236,29 @@ inline bool cache_hints_enabled() {
   return on;
 }
 
+// How many clusters of this configuration the device holds at once (asked once per device).
+template <class Cfg>
+int max_resident_clusters(const DeviceInfo& di) {
+  static thread_local int max_clusters = 0, max_clusters_dev = -1;
+  if (max_clusters_dev != di.dev) {
+    cudaLaunchConfig_t probe{};
+    probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
+    probe.blockDim = dim3(kNumThreads, 1, 1);
+    probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = Cfg::CLUSTER_CTAS; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+    probe.attrs = pa; probe.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, hgemm_tn_kernel<Cfg>, &probe) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = std::max(1, di.num_sms / Cfg::CLUSTER_CTAS * 7 / 8);
+    }
+    max_clusters = n; max_clusters_dev = di.dev;
+  }
+  return max_clusters;
+}
+
 // group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". splits > 1 requests
 // split-K (clamped to what the problem allows; only for CTA_GROUP == 1 configurations).
 template <class Cfg>
@@ -267,26 +290,12 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   if ((st = cache.get(C, M, N, 32, &mc, Cfg::EPI_N)) != kOk) return st;
 
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CLUSTER_CTAS;
-  if constexpr (Cfg::CLUSTER_CTAS > 2) {
-    // clusters must fit inside a GPC: ask the runtime how many can be resident at once (cached per device)
-    static thread_local int max_clusters = 0, max_clusters_dev = -1;
-    if (max_clusters_dev != di.dev) {
-      cudaLaunchConfig_t probe{};
-      probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
-      probe.blockDim = dim3(kNumThreads, 1, 1);
-      probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
-      cudaLaunchAttribute pa[1];
-      pa[0].id = cudaLaunchAttributeClusterDimension;
-      pa[0].val.clusterDim.x = Cfg::CLUSTER_CTAS; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
-      probe.attrs = pa; probe.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, hgemm_tn_kernel<Cfg>, &probe) != cudaSuccess || n < 1) {
-        cudaGetLastError();
-        n = std::max(1, di.num_sms / Cfg::CLUSTER_CTAS * 7 / 8);
-      }
-      max_clusters = n; max_clusters_dev = di.dev;
-    }
-    if (max_ctas <= 0 || workers > max_clusters) workers = std::min(workers, max_clusters);
+  // Clusters must fit inside a GPC, so fewer than SMs / cluster size may be resident at once. Larger clusters are
+  // always sized to what fits; CTA pairs only when stream-K is requested, whose owners wait for contributors
+  // that must therefore be running (for the plain schedule a pair that starts late is merely late).
+  const bool wants_stream_k = (splits == kStreamKTail || splits == kStreamKTailPlusWave);
+  if (Cfg::CLUSTER_CTAS > 2 || (Cfg::CLUSTER_CTAS == 2 && wants_stream_k)) {
+    workers = std::min(workers, max_resident_clusters<Cfg>(di));
   }
   Plan plan = make_plan<Cfg>(M, N, K, workers, splits);
   float* ws = nullptr;
