@@ -364,15 +364,18 @@ __device__ __forceinline__ void streamk_contribute(const EpilogueWarp& w, uint32
   if (w.lane == 0) st_release_gpu(flags + slot * kStreamKFlagsPerSlot + w.ew, 1u);
 }
 
-// Owner: accumulator + the partials of `n` contributors (slots slot0, slot0 + slot_stride, ... — increasing k),
-// summed in fp32 in that fixed order, rounded once, stored like any other tile.
-template <class Cfg, class ReleaseTmem>
+// Owner: the partials of `n` contributors (slots slot0, slot0 + slot_stride, ... — increasing k) summed in fp32 in that
+// fixed order, plus the own accumulator, rounded once, stored like any other tile. The partials were written long
+// before (they are their workers' first units), so the first chunk's are fetched BEFORE waiting for the own
+// accumulator (`wait_acc`): their L2 latency hides behind the tail of the main loop.
+template <class Cfg, class WaitAcc, class ReleaseTmem>
 __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t taddr0, const uint4* __restrict__ ws,
                                             unsigned* __restrict__ flags, int slot0, int slot_stride, int n,
                                             const CUtensorMap* tmap_c, int m0, int n0, int M, int N,
-                                            ReleaseTmem release_tmem) {
+                                            WaitAcc wait_acc, ReleaseTmem release_tmem) {
   using namespace ptx;
   using SK = StreamK<Cfg>;
+  constexpr int kBatch = SK::R4 < 8 ? SK::R4 : 8;   // quads in flight per lane: 32 registers next to the 64 sums
   if (w.lane == 0) {
     for (int p = 0; p < n; ++p) {
       const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
@@ -386,49 +389,49 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
   __syncwarp();
   const size_t warp_off = size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
   for (int j = w.j_begin; j < w.j_end; ++j) {
-    uint32_t r[SK::REGS];
-    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
-    if (j == w.j_end - 1) release_tmem();
     float f[Cfg::EPI_N];
-    if constexpr (Cfg::ACC_F32) {
 #pragma unroll
-      for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = __uint_as_float(r[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
-        const __half2 h = *reinterpret_cast<const __half2*>(&r[i]);
-        f[2 * i] = __low2float(h);
-        f[2 * i + 1] = __high2float(h);
-      }
-    }
+    for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = 0.f;
     for (int p = 0; p < n; ++p) {
       const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 + warp_off + size_t(j) * SK::CHUNK_U4;
-      // in batches of four quads, so that at most 16 loaded registers are in flight next to the 64 sums
 #pragma unroll
-      for (int b = 0; b < SK::R4 / 4; ++b) {
-        uint4 v[4];
+      for (int b = 0; b < SK::R4 / kBatch; ++b) {
+        uint4 v[kBatch];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = ld_global_cg_v4(src + (4 * b + i) * 32);
+        for (int i = 0; i < kBatch; ++i) v[i] = ld_global_cg_v4(src + (kBatch * b + i) * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kBatch; ++i) {
           const uint32_t x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if constexpr (Cfg::ACC_F32) {
-              f[4 * (4 * b + i) + c] += __uint_as_float(x[c]);
+              f[4 * (kBatch * b + i) + c] += __uint_as_float(x[c]);
             } else {
               const __half2 h = *reinterpret_cast<const __half2*>(&x[c]);
-              f[8 * (4 * b + i) + 2 * c] += __low2float(h);
-              f[8 * (4 * b + i) + 2 * c + 1] += __high2float(h);
+              f[8 * (kBatch * b + i) + 2 * c] += __low2float(h);
+              f[8 * (kBatch * b + i) + 2 * c + 1] += __high2float(h);
             }
           }
         }
         __syncwarp();   // keeps the compiler from hoisting the next batch's loads above these sums
       }
     }
+    if (j == w.j_begin) wait_acc();
+    uint32_t r[SK::REGS];
+    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+    if (j == w.j_end - 1) release_tmem();
     uint32_t packed[Cfg::EPI_N / 2];
+    if constexpr (Cfg::ACC_F32) {
 #pragma unroll
-    for (int i = 0; i < Cfg::EPI_N / 2; ++i) packed[i] = pack_f16x2_rn(f[2 * i], f[2 * i + 1]);
+      for (int i = 0; i < Cfg::EPI_N / 2; ++i)
+        packed[i] = pack_f16x2_rn(f[2 * i] + __uint_as_float(r[2 * i]), f[2 * i + 1] + __uint_as_float(r[2 * i + 1]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&r[i]);
+        packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(h), f[2 * i + 1] + __high2float(h));
+      }
+    }
     epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
   }
   // lower the flags again: this warp is their only reader, and the next writer is a later launch
@@ -643,9 +646,33 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
         if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
-      mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
-      tc_fence_after_sync();
       const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
+      // the MMA warp's commit: this unit's accumulator is complete
+      auto wait_acc = [&] {
+        mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
+        tc_fence_after_sync();
+      };
+      // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
+      auto release_tmem = [&] {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
+          else mbar_arrive(tmem_empty0 + 8 * acc);
+        }
+      };
+      [[maybe_unused]] uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
+      [[maybe_unused]] unsigned* sk_flags = splitk_ctr + 2 * kMaxSplitTiles;
+      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64) {
+        if (sk_tiles > 0 && u.kb0 == 0 && u.kb1 < num_k_blocks) {   // stream-K: the head of a tile, which owns it
+          const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
+          streamk_own<Cfg>(ew, taddr0, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m0, n0, M, N,
+                           wait_acc, release_tmem);
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
+      wait_acc();
       if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
         if (splits > 1 && cluster_reduce) {
           cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
@@ -658,26 +685,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
-      // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
-      auto release_tmem = [&] {
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
-          else mbar_arrive(tmem_empty0 + 8 * acc);
-        }
-      };
       if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64) {
-        if (u.kb0 > 0 || u.kb1 < num_k_blocks) {   // stream-K: a partial sum of the tile (never taken when sk_tiles == 0)
-          uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
-          unsigned* flags = splitk_ctr + 2 * kMaxSplitTiles;
-          if (u.kb0 > 0) {
-            streamk_contribute<Cfg>(ew, taddr0, ws4, flags, worker * CG + int(cta_rank), release_tmem);
-          } else {
-            const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
-            streamk_own<Cfg>(ew, taddr0, ws4, flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m0, n0, M, N,
-                             release_tmem);
-          }
+        if (sk_tiles > 0 && u.kb0 > 0) {   // stream-K: a later part of a tile's k-range, handed to the tile's owner
+          streamk_contribute<Cfg>(ew, taddr0, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
           if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
           continue;
         }
