@@ -17,9 +17,9 @@ int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int
   using namespace b200;
   int st;
   switch (id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN)                                                      \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)                                                      \
   case ID:                                                                                         \
-    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
+    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN, MR>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
     break;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
@@ -46,7 +46,7 @@ int b200_hgemm_num_configs(void) { return b200::kNumConfigs; }
 
 int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group) {
   switch (config_id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN)  \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)  \
   case ID:                             \
     if (bn) *bn = BN;                  \
     if (stages) *stages = STAGES;      \
@@ -61,11 +61,23 @@ int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group) 
 
 int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n) {
   switch (config_id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN) \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR) \
   case ID:                                    \
     if (cluster_m) *cluster_m = CM;           \
     if (cluster_n) *cluster_n = CN;           \
     return 0;
+    B200_HGEMM_CONFIGS(B200_CASE)
+#undef B200_CASE
+    default:
+      return b200::host::kBadConfig;
+  }
+}
+
+int b200_hgemm_config_m_rep(int config_id) {
+  switch (config_id) {
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR) \
+  case ID:                                        \
+    return MR;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
     default:

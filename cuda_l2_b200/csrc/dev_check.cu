@@ -293,9 +293,10 @@ static int do_sweep(int acc, int M, int N, int K, int iters) {
   const int gms[] = {1, 2, 4, 8, 16, 32};
   for (int c = 0; c < ncfg; ++c) {
     int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
-    if ((M + 127) / 128 < cg * cm || (N + bn - 1) / bn < cn) continue;
+    const int mr = b200_hgemm_config_m_rep(c);
+    if ((M + 127) / 128 < cg * cm * mr || (N + bn - 1) / bn < cn) continue;
     for (int gm : gms) {
-      const int nm = (M + 128 * cg * cm - 1) / (128 * cg * cm);
+      const int nm = (M + 128 * cg * cm * mr - 1) / (128 * cg * cm * mr);
       if (gm > 1 && gm / 2 >= nm) continue;   // wider than the problem: same schedule as the previous one
       int st = run_ours(acc, c, p, gm);
       cudaError_t e = cudaDeviceSynchronize();
@@ -345,12 +346,14 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     std::vector<Cand> all;
     for (int c = 0; c < ncfg; ++c) {
       int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
-      if ((p.M + 127) / 128 < cg * cm || (p.N + bn - 1) / bn < cn) continue;   // part of the cluster would only see padding
+      const int mr = b200_hgemm_config_m_rep(c);
+      if ((p.M + 127) / 128 < cg * cm * mr || (p.N + bn - 1) / bn < cn) continue;   // part of the tile would only see padding
+      if (mr > 1 && p.K < 2048) continue;   // no accumulator ring: the epilogue is exposed, only a long K amortises it
       // pair + multicast: exact, but slower than plain pairs in every event-time run; the wall-metric mode keeps them,
       // because they move the fewest bytes per FLOP (what cuBLAS's 2x2_2cta kernels do) and that is what counts at the power cap
       if (cg == 2 && cm * cn > 1 && !wall_metric) continue;
-      const bool plain = (cm * cn == 1) && bn >= 64;
-      const int nm = (p.M + 128 * cg * cm - 1) / (128 * cg * cm);
+      const bool plain = (cm * cn == 1) && bn >= 64 && mr == 1;
+      const int nm = (p.M + 128 * cg * cm * mr - 1) / (128 * cg * cm * mr);
       const int nn = (p.N + bn * cn - 1) / (bn * cn);
       std::vector<std::pair<int, int>> cands = {{0, 1}};   // (group_m, splits)
       if (nm * nn > 148 / (cg * cm * cn) && nm > 1 && nn > 1) {

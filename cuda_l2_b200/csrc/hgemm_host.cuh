@@ -238,7 +238,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     if (max_ctas <= 0 || workers > max_clusters) workers = std::min(workers, max_clusters);
   }
   if (workers < 1) workers = 1;
-  if (Cfg::MCAST_CTAS > 1 || Cfg::BN < 64) splits = 1;   // split-K is wired for plain configs with BN >= 64
+  if (Cfg::MCAST_CTAS > 1 || Cfg::BN < 64 || Cfg::M_REP > 1) splits = 1;   // split-K is wired for plain configs with BN >= 64
   // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
   int cluster_reduce = 0;
   if (splits < -1) {

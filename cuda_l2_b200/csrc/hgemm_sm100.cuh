@@ -73,7 +73,7 @@ __device__ __forceinline__ void trace_value(int slot, unsigned long long v) {
 #define B200_TRACE_ONLY(...)
 #endif
 
-template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1>
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1, int M_REP_ = 1>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
   static constexpr int STAGES = STAGES_;
@@ -87,11 +87,18 @@ struct Config {
   static constexpr int CLUSTER_N = CLUSTER_N_;
   static constexpr int MCAST_CTAS = CLUSTER_M * CLUSTER_N;
   static constexpr int CLUSTER_CTAS = CTA_GROUP * MCAST_CTAS;
-  static constexpr int TILE_M = kBlockM * CTA_GROUP;
+  // M_REP = 2: every CTA owns 256 rows — two 128-row MMAs per k-step that share the B tile in shared memory and fill
+  // two accumulators — so a CTA pair covers 512 x BN and each B byte fetched from L2 feeds twice the MMA work (the
+  // shape of cuBLAS's largest kernel, nvjet_hsh_256x256_64x4_2x1_2cta). With BN = 256 the two accumulators fill all
+  // 512 TMEM columns: no accumulator ring, the epilogue of a tile is not overlapped with the next main loop, which
+  // only a long K amortises. No split-K / stream-K in this mode.
+  static constexpr int M_REP = M_REP_;
+  static constexpr int CTA_M = kBlockM * M_REP;             // rows per CTA
+  static constexpr int TILE_M = CTA_M * CTA_GROUP;
   static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA holds per stage
-  static constexpr int A_BOX_ROWS = kBlockM / CLUSTER_N;    // A rows each CTA loads per stage
+  static constexpr int A_BOX_ROWS = CTA_M / CLUSTER_N;      // A rows each CTA loads per stage
   static constexpr int B_BOX_ROWS = LOAD_N / CLUSTER_M;     // B rows each CTA loads per stage
-  static constexpr int A_STAGE_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int A_STAGE_BYTES = CTA_M * kBlockK * 2;
   static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_N = BN < 64 ? BN : 64;            // columns per epilogue step / TMA store box
@@ -103,17 +110,21 @@ struct Config {
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static constexpr int TMEM_COLS_USED = kAccStages * BN;
+  static constexpr int ACC_COLS = M_REP * BN;                // TMEM columns of one accumulator stage
+  static constexpr int ACC_STAGES = (kAccStages * ACC_COLS <= 512) ? kAccStages : 1;   // ring depth that fits TMEM
+  static constexpr int TMEM_COLS_USED = ACC_STAGES * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                  : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(BN == 32 || BN % 64 == 0, "tile N is 32 or a multiple of 64");
   static_assert(BN >= 32 && BN <= 256 && (BN % 16) == 0, "UMMA N constraints");
   static_assert(CLUSTER_CTAS <= 8, "portable cluster size");
   static_assert(A_BOX_ROWS % 8 == 0 && B_BOX_ROWS % 8 == 0, "slices must cover whole 8-row swizzle atoms");
+  static_assert(M_REP == 1 || M_REP == 2, "one or two 128-row blocks per CTA");
+  static_assert(A_BOX_ROWS <= 256 && B_BOX_ROWS <= 256, "TMA box dimension limit");
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
-  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");   // ACC_STAGES <= kAccStages
 };
 
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
@@ -340,6 +351,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   constexpr int CM = Cfg::CLUSTER_M;
   constexpr int CN = Cfg::CLUSTER_N;
   constexpr bool kMcast = Cfg::MCAST_CTAS > 1;
+  constexpr int AS = Cfg::ACC_STAGES;
+  constexpr int MR = Cfg::M_REP;
   using namespace ptx;
 
   extern __shared__ uint8_t smem_raw[];
@@ -386,7 +399,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx (the leader's, for a pair)
       mbar_init(bar_empty + 8 * s, kMcast ? CM + CN - 1 : 1);   // tcgen05.commit of every CTA this stage is shared with
     }
-    for (int a = 0; a < kAccStages; ++a) {
+    for (int a = 0; a < AS; ++a) {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
@@ -434,7 +447,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       const int kb0 = (u - t * splits) * kb_per_split;
       const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM + cn * Cfg::A_BOX_ROWS;
+      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M + cn * Cfg::A_BOX_ROWS;
       const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -457,7 +470,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      constexpr uint32_t idesc = make_idesc(kBlockM * CG, BN, Cfg::ACC_F32);   // one MMA covers 128 rows per CTA of the group
       const uint64_t desc_a0 = make_smem_desc(smem_a);
       const uint64_t desc_b0 = make_smem_desc(smem_b);
       // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
@@ -479,7 +492,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
         mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
@@ -492,6 +505,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            if constexpr (MR == 2) {
+              // the second 128-row block of this CTA's A tile (16 KB further into the stage) -> the second accumulator
+              constexpr uint64_t kSecondBlock = uint64_t((kBlockM * kBlockK * 2) >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_f16<CG>(tmem_d + BN, da + kSecondBlock + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            }
             // free the smem slot everywhere it is shared once these MMAs have read it
             if constexpr (CG == 2 || kMcast) umma_commit_mcast<CG>(bar_empty + 8 * stage, mask_free);
             else umma_commit<CG>(bar_empty + 8 * stage);
@@ -503,7 +523,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        if (++acc == AS) { acc = 0; acc_phase ^= 1; }
         B200_TRACE_ONLY(++trace_units;)
       }
       B200_TRACE_ONLY(if (lane == 0) { B200_TRACE(5); B200_TRACE_VALUE(9, trace_kb); B200_TRACE_VALUE(11, trace_units); })
@@ -528,17 +548,17 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     for (int u = worker; u < num_units; u += num_workers) {
       const int t = u / splits;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
-      const int m0 = m_tile0 + q * 32;
+      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M;
       const int n0 = (tc.n_blk * CN + cn) * BN;
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
         if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
       mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
       tc_fence_after_sync();
       B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) { if (trace_first) { B200_TRACE(6); trace_first = false; } B200_TRACE(10); })
-      const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+      const uint32_t taddr_acc = tmem_base + uint32_t(acc * Cfg::ACC_COLS) + (uint32_t(q * 32) << 16);
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
+        const uint32_t taddr0 = taddr_acc;
         if (splits > 1 && cluster_reduce) {
           cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
           ck_m_base = m_tile0; ck_n0 = n0; ck_split = u - t * splits;
@@ -550,6 +570,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
+#pragma unroll
+      for (int r = 0; r < MR; ++r) {   // the 128-row blocks of this CTA's tile, one accumulator each
+      const uint32_t taddr0 = taddr_acc + uint32_t(r * BN);
+      const int m0 = m_tile0 + r * kBlockM + q * 32;
       for (int j = j_begin; j < j_end; ++j) {
         uint32_t packed[EN / 2];
         if constexpr (Cfg::ACC_F32) {
@@ -573,7 +597,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == j_end - 1) {
+        if (j == j_end - 1 && r == MR - 1) {
           // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
@@ -599,7 +623,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           tma_store_commit();
         }
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      if (++acc == AS) { acc = 0; acc_phase ^= 1; }
     }
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
@@ -608,7 +633,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
     if (splits > 1 && cluster_reduce) {
       __syncwarp();
       cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
