@@ -84,6 +84,25 @@ def build_dev_check(verbose: bool = False, force: bool = False) -> Path:
     return out
 
 
+def build_trace(verbose: bool = False, force: bool = False) -> Path:
+    """Developer build with per-CTA phase timestamps (-DB200_HGEMM_TRACE): libb200_hgemm_trace.so + dev_check_trace.
+
+    Not part of build_all(): the product library contains no instrumentation."""
+    LIB_DIR.mkdir(exist_ok=True)
+    build_baselines(verbose, force)
+    lib = LIB_DIR / "libb200_hgemm_trace.so"
+    src = CSRC / "b200_hgemm_capi.cu"
+    if force or _stale(lib, [src] + _headers()):
+        _run([nvcc_path(), *ARCH_FLAGS, *COMMON, "-DB200_HGEMM_TRACE", "--shared", "-o", str(lib), str(src)], verbose)
+    out = LIB_DIR / "dev_check_trace"
+    dsrc = CSRC / "dev_check.cu"
+    if force or _stale(out, [dsrc, lib] + _headers()):
+        _run([nvcc_path(), *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", "-DB200_HGEMM_TRACE", "-o", str(out), str(dsrc),
+              f"-L{LIB_DIR}", "-lb200_hgemm_trace", "-lb200_baselines", "-lcublas", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"],
+             verbose)
+    return out
+
+
 def build_all(verbose: bool = False, force: bool = False) -> dict[str, Path]:
     out = {"capi": build_capi(verbose, force)}
     if (CSRC / "b200_baselines_capi.cu").exists():

@@ -42,6 +42,7 @@ def hgemm_lib() -> ctypes.CDLL:
         lib.b200_hgemm_num_configs.restype = i
         lib.b200_hgemm_config_info.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_config_cluster.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i)]
+        lib.b200_hgemm_config_m_rep.argtypes = [i]
         lib.b200_hgemm_select_config.argtypes = [i, i, i, i]
         lib.b200_hgemm_select.argtypes = [i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_run_config.argtypes = [i, i, vp, vp, vp, i, i, i, i, i, i, vp]
@@ -77,7 +78,7 @@ def exported_symbols() -> dict[str, list[str]]:
     return {
         "libb200_hgemm.so": [
             "b200_hgemm_f32acc", "b200_hgemm_f16acc", "b200_hgemm_num_configs", "b200_hgemm_config_info",
-            "b200_hgemm_config_cluster",
+            "b200_hgemm_config_cluster", "b200_hgemm_config_m_rep",
             "b200_hgemm_select_config", "b200_hgemm_select", "b200_hgemm_run_config", "b200_hgemm_host", "b200_hgemm_launch_count",
             "b200_hgemm_strerror", "b200_hgemm_schedule_units",
         ],
@@ -151,7 +152,7 @@ def configs() -> list[dict]:
         cm, cn = ctypes.c_int(), ctypes.c_int()
         lib.b200_hgemm_config_cluster(cid, ctypes.byref(cm), ctypes.byref(cn))
         out.append({"id": cid, "bn": bn.value, "stages": st.value, "cta_group": cg.value,
-                    "cluster_m": cm.value, "cluster_n": cn.value})
+                    "cluster_m": cm.value, "cluster_n": cn.value, "m_rep": lib.b200_hgemm_config_m_rep(cid)})
     return out
 
 

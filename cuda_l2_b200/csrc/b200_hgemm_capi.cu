@@ -17,9 +17,9 @@ int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int
   using namespace b200;
   int st;
   switch (id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN)                                                      \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)                                                      \
   case ID:                                                                                         \
-    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
+    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN, MR>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
     break;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
@@ -69,7 +69,7 @@ int b200_hgemm_num_configs(void) { return b200::kNumConfigs; }
 
 int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group) {
   switch (config_id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN)  \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)  \
   case ID:                             \
     if (bn) *bn = BN;                  \
     if (stages) *stages = STAGES;      \
@@ -84,7 +84,7 @@ int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group) 
 
 int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n) {
   switch (config_id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN) \
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR) \
   case ID:                                    \
     if (cluster_m) *cluster_m = CM;           \
     if (cluster_n) *cluster_n = CN;           \
@@ -100,10 +100,22 @@ int b200_hgemm_schedule_units(int config_id, int M, int N, int K, int splits, in
                               int max_units, int* num_workers, int* sk_tiles, int* contributors) {
   if (M <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return b200::host::kBadShape;
   switch (config_id) {
-#define B200_CASE(ID, BN, STAGES, CG, CM, CN)                                                                   \
-  case ID:                                                                                                      \
-    return schedule_units<b200::Config<BN, STAGES, CG, true, CM, CN>>(M, N, K, splits, num_sms, worker, units, \
-                                                                      max_units, num_workers, sk_tiles, contributors);
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)                                                                   \
+  case ID:                                                                                                          \
+    return schedule_units<b200::Config<BN, STAGES, CG, true, CM, CN, MR>>(M, N, K, splits, num_sms, worker, units, \
+                                                                          max_units, num_workers, sk_tiles, contributors);
+    B200_HGEMM_CONFIGS(B200_CASE)
+#undef B200_CASE
+    default:
+      return b200::host::kBadConfig;
+  }
+}
+
+int b200_hgemm_config_m_rep(int config_id) {
+  switch (config_id) {
+#define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR) \
+  case ID:                                        \
+    return MR;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
     default:
@@ -178,6 +190,35 @@ int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* h
   e = cudaStreamSynchronize(0);
   return e == cudaSuccess ? 0 : int(e);
 }
+
+#ifdef B200_HGEMM_TRACE
+// Developer-only entry points of libb200_hgemm_trace.so (see kTraceSlots in hgemm_sm100.cuh); not part of the C ABI.
+static unsigned long long* g_trace_dev = nullptr;
+static int g_trace_ctas = 0;
+int b200_hgemm_trace_slots(void) { return b200::kTraceSlots; }
+int b200_hgemm_trace_arm(int max_ctas) {   // zero the buffer and point the kernels at it (max_ctas <= 0: disarm)
+  unsigned long long* none = nullptr;
+  if (max_ctas <= 0) return int(cudaMemcpyToSymbol(b200::g_trace_buf, &none, sizeof(none)));
+  const size_t bytes = size_t(max_ctas) * b200::kTraceSlots * 2 * sizeof(unsigned long long);
+  if (max_ctas > g_trace_ctas) {
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    g_trace_dev = nullptr; g_trace_ctas = 0;
+    cudaError_t e = cudaMalloc(&g_trace_dev, bytes);
+    if (e != cudaSuccess) return int(e);
+    g_trace_ctas = max_ctas;
+  }
+  cudaError_t e = cudaMemset(g_trace_dev, 0, bytes);
+  if (e != cudaSuccess) return int(e);
+  return int(cudaMemcpyToSymbol(b200::g_trace_buf, &g_trace_dev, sizeof(g_trace_dev)));
+}
+int b200_hgemm_trace_read(unsigned long long* out, int ctas) {
+  if (!g_trace_dev || ctas > g_trace_ctas) return b200::host::kBadShape;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return int(e);
+  return int(cudaMemcpy(out, g_trace_dev, size_t(ctas) * b200::kTraceSlots * 2 * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost));
+}
+#endif
 
 unsigned long long b200_hgemm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -169,7 +169,7 @@ inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
 template <class Cfg>
 int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   if (splits <= 1 || Cfg::CTA_GROUP != 1) return 1;
-  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);   // CTA_GROUP == 1: callers exclude M_REP > 1
   const int nkb = (K + kBlockK - 1) / kBlockK;
   if (tiles > kMaxSplitTiles) return 1;
   splits = std::min(splits, std::min(num_sms / tiles, std::min(nkb, 32)));   // <= 32: the slices of all partials must fit the pipeline smem
@@ -201,7 +201,7 @@ Plan make_plan(int M, int N, int K, int workers_avail, int splits) {
   p.num_tiles = num_m_blocks * num_n_blocks;
   p.nkb = (K + kBlockK - 1) / kBlockK;
   p.workers = std::max(workers_avail, 1);
-  const bool plain = Cfg::MCAST_CTAS == 1 && Cfg::BN >= 64;   // the K-decompositions are wired for these
+  const bool plain = Cfg::MCAST_CTAS == 1 && Cfg::BN >= 64 && Cfg::M_REP == 1;   // the K-decompositions are wired for these
   int sk_mode = 0;
   if (splits == kStreamKTail || splits == kStreamKTailPlusWave) { sk_mode = splits; splits = 1; }
   if (!plain) splits = 1;

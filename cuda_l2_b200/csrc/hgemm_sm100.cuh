@@ -48,7 +48,36 @@ constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
 
-template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1>
+// Developer instrumentation (only in builds with -DB200_HGEMM_TRACE, i.e. libb200_hgemm_trace.so; the product build
+// contains none of it): per-CTA timestamps of the kernel's phases, read back by `dev_check_trace trace`.
+//   slot 0 entry | 1 setup done | 2 first TMA issued | 3 last TMA issued | 4 first stage landed (MMA warp)
+//   5 last MMA commit issued | 6 first accumulator complete (epilogue) | 7 epilogue drained | 8 after the teardown
+//   barrier | 9 k-blocks issued (a count) | 10 last accumulator complete (epilogue) | 11 units run (a count)
+constexpr int kTraceSlots = 12;      // each slot: {%globaltimer ns, clock64}
+#ifdef B200_HGEMM_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;   // [gridDim.x][kTraceSlots][2], zeroed by the host before the launch
+__device__ __forceinline__ void trace_mark(int slot) {
+  if (g_trace_buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* e = g_trace_buf + (size_t(blockIdx.x) * kTraceSlots + slot) * 2;
+    e[0] = t;
+    e[1] = (unsigned long long)clock64();
+  }
+}
+__device__ __forceinline__ void trace_value(int slot, unsigned long long v) {
+  if (g_trace_buf) g_trace_buf[(size_t(blockIdx.x) * kTraceSlots + slot) * 2] = v;
+}
+#define B200_TRACE(slot) ::b200::trace_mark(slot)
+#define B200_TRACE_VALUE(slot, v) ::b200::trace_value(slot, v)
+#define B200_TRACE_ONLY(...) __VA_ARGS__
+#else
+#define B200_TRACE(slot) ((void)0)
+#define B200_TRACE_VALUE(slot, v) ((void)0)
+#define B200_TRACE_ONLY(...)
+#endif
+
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1, int M_REP_ = 1>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
   static constexpr int STAGES = STAGES_;
@@ -62,11 +91,18 @@ struct Config {
   static constexpr int CLUSTER_N = CLUSTER_N_;
   static constexpr int MCAST_CTAS = CLUSTER_M * CLUSTER_N;
   static constexpr int CLUSTER_CTAS = CTA_GROUP * MCAST_CTAS;
-  static constexpr int TILE_M = kBlockM * CTA_GROUP;
+  // M_REP = 2: every CTA owns 256 rows — two 128-row MMAs per k-step that share the B tile in shared memory and fill
+  // two accumulators — so a CTA pair covers 512 x BN and each B byte fetched from L2 feeds twice the MMA work (the
+  // shape of cuBLAS's largest kernel, nvjet_hsh_256x256_64x4_2x1_2cta). With BN = 256 the two accumulators fill all
+  // 512 TMEM columns: no accumulator ring, the epilogue of a tile is not overlapped with the next main loop, which
+  // only a long K amortises. No split-K / stream-K in this mode.
+  static constexpr int M_REP = M_REP_;
+  static constexpr int CTA_M = kBlockM * M_REP;             // rows per CTA
+  static constexpr int TILE_M = CTA_M * CTA_GROUP;
   static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA holds per stage
-  static constexpr int A_BOX_ROWS = kBlockM / CLUSTER_N;    // A rows each CTA loads per stage
+  static constexpr int A_BOX_ROWS = CTA_M / CLUSTER_N;      // A rows each CTA loads per stage
   static constexpr int B_BOX_ROWS = LOAD_N / CLUSTER_M;     // B rows each CTA loads per stage
-  static constexpr int A_STAGE_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int A_STAGE_BYTES = CTA_M * kBlockK * 2;
   static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_N = BN < 64 ? BN : 64;            // columns per epilogue step / TMA store box
@@ -78,17 +114,21 @@ struct Config {
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static constexpr int TMEM_COLS_USED = kAccStages * BN;
+  static constexpr int ACC_COLS = M_REP * BN;                // TMEM columns of one accumulator stage
+  static constexpr int ACC_STAGES = (kAccStages * ACC_COLS <= 512) ? kAccStages : 1;   // ring depth that fits TMEM
+  static constexpr int TMEM_COLS_USED = ACC_STAGES * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                  : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(BN == 32 || BN % 64 == 0, "tile N is 32 or a multiple of 64");
   static_assert(BN >= 32 && BN <= 256 && (BN % 16) == 0, "UMMA N constraints");
   static_assert(CLUSTER_CTAS <= 8, "portable cluster size");
   static_assert(A_BOX_ROWS % 8 == 0 && B_BOX_ROWS % 8 == 0, "slices must cover whole 8-row swizzle atoms");
+  static_assert(M_REP == 1 || M_REP == 2, "one or two 128-row blocks per CTA");
+  static_assert(A_BOX_ROWS <= 256 && B_BOX_ROWS <= 256, "TMA box dimension limit");
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
-  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");   // ACC_STAGES <= kAccStages
 };
 
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
@@ -351,6 +391,7 @@ __device__ __forceinline__ void streamk_contribute(const EpilogueWarp& w, uint32
   using namespace ptx;
   using SK = StreamK<Cfg>;
   uint4* base = ws + size_t(slot) * SK::SLOT_U4 + size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+#pragma unroll 1   // one chunk image (64 registers) at a time
   for (int j = w.j_begin; j < w.j_end; ++j) {
     uint32_t r[SK::REGS];
     streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
@@ -375,7 +416,6 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
                                             WaitAcc wait_acc, ReleaseTmem release_tmem) {
   using namespace ptx;
   using SK = StreamK<Cfg>;
-  constexpr int kBatch = SK::R4 < 8 ? SK::R4 : 8;   // quads in flight per lane: 32 registers next to the 64 sums
   if (w.lane == 0) {
     for (int p = 0; p < n; ++p) {
       const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
@@ -388,48 +428,64 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
   }
   __syncwarp();
   const size_t warp_off = size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+  // A chunk is summed in pieces of kPiece columns so that (sums + values in flight + own accumulator) stays near the
+  // register footprint of the plain epilogue: fp32 images in two pieces of 32 columns, fp16 images (half the
+  // registers) in one piece of 64.
+  constexpr int kPiece = Cfg::ACC_F32 ? 32 : 64;                  // columns
+  constexpr int kPieceQuads = SK::R4 * kPiece / Cfg::EPI_N;       // image quads per piece (8 in both cases)
+  constexpr int kBatch = 4;                                       // quads in flight per lane
+#pragma unroll 1
   for (int j = w.j_begin; j < w.j_end; ++j) {
-    float f[Cfg::EPI_N];
+    uint32_t packed[Cfg::EPI_N / 2];
 #pragma unroll
-    for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = 0.f;
-    for (int p = 0; p < n; ++p) {
-      const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 + warp_off + size_t(j) * SK::CHUNK_U4;
+    for (int h = 0; h < Cfg::EPI_N / kPiece; ++h) {
+      float f[kPiece];
 #pragma unroll
-      for (int b = 0; b < SK::R4 / kBatch; ++b) {
-        uint4 v[kBatch];
+      for (int i = 0; i < kPiece; ++i) f[i] = 0.f;
+      for (int p = 0; p < n; ++p) {
+        const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 + warp_off + size_t(j) * SK::CHUNK_U4 +
+                           size_t(h * kPieceQuads) * 32;
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) v[i] = ld_global_cg_v4(src + (kBatch * b + i) * 32);
+        for (int b = 0; b < kPieceQuads / kBatch; ++b) {
+          uint4 v[kBatch];
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-          const uint32_t x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          for (int i = 0; i < kBatch; ++i) v[i] = ld_global_cg_v4(src + (kBatch * b + i) * 32);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if constexpr (Cfg::ACC_F32) {
-              f[4 * (kBatch * b + i) + c] += __uint_as_float(x[c]);
-            } else {
-              const __half2 h = *reinterpret_cast<const __half2*>(&x[c]);
-              f[8 * (kBatch * b + i) + 2 * c] += __low2float(h);
-              f[8 * (kBatch * b + i) + 2 * c + 1] += __high2float(h);
+          for (int i = 0; i < kBatch; ++i) {
+            const uint32_t x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if constexpr (Cfg::ACC_F32) {
+                f[4 * (kBatch * b + i) + c] += __uint_as_float(x[c]);
+              } else {
+                const __half2 hh = *reinterpret_cast<const __half2*>(&x[c]);
+                f[8 * (kBatch * b + i) + 2 * c] += __low2float(hh);
+                f[8 * (kBatch * b + i) + 2 * c + 1] += __high2float(hh);
+              }
             }
           }
+          __syncwarp();   // keeps the compiler from hoisting the next batch's loads above these sums
         }
-        __syncwarp();   // keeps the compiler from hoisting the next batch's loads above these sums
       }
-    }
-    if (j == w.j_begin) wait_acc();
-    uint32_t r[SK::REGS];
-    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
-    if (j == w.j_end - 1) release_tmem();
-    uint32_t packed[Cfg::EPI_N / 2];
-    if constexpr (Cfg::ACC_F32) {
+      if (j == w.j_begin && h == 0) wait_acc();
+      const bool last = (j == w.j_end - 1) && (h == Cfg::EPI_N / kPiece - 1);
+      if constexpr (Cfg::ACC_F32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + j * Cfg::EPI_N + 32 * h, v);
+        tmem_ld_wait();
+        if (last) release_tmem();
 #pragma unroll
-      for (int i = 0; i < Cfg::EPI_N / 2; ++i)
-        packed[i] = pack_f16x2_rn(f[2 * i] + __uint_as_float(r[2 * i]), f[2 * i + 1] + __uint_as_float(r[2 * i + 1]));
-    } else {
+        for (int i = 0; i < 16; ++i)
+          packed[16 * h + i] = pack_f16x2_rn(f[2 * i] + __uint_as_float(v[2 * i]), f[2 * i + 1] + __uint_as_float(v[2 * i + 1]));
+      } else {
+        uint32_t r[SK::REGS];
+        streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+        if (last) release_tmem();
 #pragma unroll
-      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
-        const __half2 h = *reinterpret_cast<const __half2*>(&r[i]);
-        packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(h), f[2 * i + 1] + __high2float(h));
+        for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+          const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
+          packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+        }
       }
     }
     epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
@@ -460,6 +516,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   constexpr int CM = Cfg::CLUSTER_M;
   constexpr int CN = Cfg::CLUSTER_N;
   constexpr bool kMcast = Cfg::MCAST_CTAS > 1;
+  constexpr int AS = Cfg::ACC_STAGES;
+  constexpr int MR = Cfg::M_REP;
   using namespace ptx;
 
   extern __shared__ uint8_t smem_raw[];
@@ -477,6 +535,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(0);)
   // Position inside the cluster: rank = (cm + CLUSTER_M * cn) * CTA_GROUP + (position inside the MMA pair).
   // (A cluster split-K launch of a plain config also has ranks, but does not use them here.)
   const uint32_t cluster_rank = (Cfg::CLUSTER_CTAS > 1) ? cluster_ctarank() : 0u;
@@ -504,7 +563,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx (the leader's, for a pair)
       mbar_init(bar_empty + 8 * s, kMcast ? CM + CN - 1 : 1);   // tcgen05.commit of every CTA this stage is shared with
     }
-    for (int a = 0; a < kAccStages; ++a) {
+    for (int a = 0; a < AS; ++a) {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
@@ -524,6 +583,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
   int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
 
@@ -545,11 +605,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const uint32_t a_slice = uint32_t(cn) * (Cfg::A_BOX_ROWS * kBlockK * 2);
     const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
     int stage = 0; uint32_t phase = 0;
+    B200_TRACE_ONLY(bool trace_first = true;)
     WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
     WorkUnit u;
     while (work.next(u)) {
       const TileCoord tc = tile_coord(u.tile, num_m_blocks, num_n_blocks, group_m);
-      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM + cn * Cfg::A_BOX_ROWS;
+      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M + cn * Cfg::A_BOX_ROWS;
       const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
       for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -561,16 +622,18 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tma_load_2d_hint<CG>(dst_a, &tmap_a, full_uc + 8 * stage, kb * kBlockK, m0, hint_a);
           if constexpr (CM > 1) tma_load_2d_mcast_hint<CG>(dst_b, &tmap_b, full_mc + 8 * stage, kb * kBlockK, n0, mask_b, hint_b);
           else tma_load_2d_hint<CG>(dst_b, &tmap_b, full_uc + 8 * stage, kb * kBlockK, n0, hint_b);
+          B200_TRACE_ONLY(if (trace_first) { B200_TRACE(2); trace_first = false; })
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    B200_TRACE_ONLY(if (lane == 0) B200_TRACE(3);)
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      constexpr uint32_t idesc = make_idesc(kBlockM * CG, BN, Cfg::ACC_F32);   // one MMA covers 128 rows per CTA of the group
       const uint64_t desc_a0 = make_smem_desc(smem_a);
       const uint64_t desc_b0 = make_smem_desc(smem_b);
       // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
@@ -586,16 +649,18 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      B200_TRACE_ONLY(bool trace_first = true; unsigned long long trace_kb = 0, trace_units = 0;)
       WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
       WorkUnit u;
       while (work.next(u)) {
         const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
+          B200_TRACE_ONLY(if (trace_first) { if (lane == 0) B200_TRACE(4); trace_first = false; } ++trace_kb;)
           if (elect_one()) {
             // stage s lives (A_STAGE_BYTES >> 4) further along in the descriptor's (addr >> 4) field;
             // +32 B per K step inside the 128 B swizzle row == +2 in that field
@@ -604,6 +669,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            if constexpr (MR == 2) {
+              // the second 128-row block of this CTA's A tile (16 KB further into the stage) -> the second accumulator
+              constexpr uint64_t kSecondBlock = uint64_t((kBlockM * kBlockK * 2) >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_f16<CG>(tmem_d + BN, da + kSecondBlock + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            }
             // free the smem slot everywhere it is shared once these MMAs have read it
             if constexpr (CG == 2 || kMcast) umma_commit_mcast<CG>(bar_empty + 8 * stage, mask_free);
             else umma_commit<CG>(bar_empty + 8 * stage);
@@ -615,8 +687,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        if (++acc == AS) { acc = 0; acc_phase ^= 1; }
+        B200_TRACE_ONLY(++trace_units;)
       }
+      B200_TRACE_ONLY(if (lane == 0) { B200_TRACE(5); B200_TRACE_VALUE(9, trace_kb); B200_TRACE_VALUE(11, trace_units); })
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue: TMEM -> registers -> (cvt) -> swizzled smem -> TMA store =====
@@ -633,6 +707,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const int j_end = min(Cfg::EPI_CHUNKS, j_begin + CPG);
     const bool working = eg < Cfg::EPI_GROUPS;      // narrow tiles keep the second set of warps idle
     int acc = 0; uint32_t acc_phase = 0;
+    B200_TRACE_ONLY(bool trace_first = true;)
     const EpilogueWarp ew{q, warp - kEpiWarp0, lane, j_begin, j_end, epi_buf, row_off, sw};
     if (working) {
     WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
@@ -640,17 +715,17 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     while (work.next(u)) {
       const int t = u.tile;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
-      const int m0 = m_tile0 + q * 32;
+      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M;
       const int n0 = (tc.n_blk * CN + cn) * BN;
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
         if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
-      const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
+      const uint32_t taddr_acc = tmem_base + uint32_t(acc * Cfg::ACC_COLS) + (uint32_t(q * 32) << 16);
       // the MMA warp's commit: this unit's accumulator is complete
       auto wait_acc = [&] {
         mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
         tc_fence_after_sync();
+        B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) { if (trace_first) { B200_TRACE(6); trace_first = false; } B200_TRACE(10); })
       };
       // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
       auto release_tmem = [&] {
@@ -663,35 +738,39 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       };
       [[maybe_unused]] uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
       [[maybe_unused]] unsigned* sk_flags = splitk_ctr + 2 * kMaxSplitTiles;
-      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64) {
+      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && MR == 1) {
         if (sk_tiles > 0 && u.kb0 == 0 && u.kb1 < num_k_blocks) {   // stream-K: the head of a tile, which owns it
           const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
-          streamk_own<Cfg>(ew, taddr0, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m0, n0, M, N,
-                           wait_acc, release_tmem);
-          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          streamk_own<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m_tile0 + q * 32,
+                           n0, M, N, wait_acc, release_tmem);
+          if (++acc == AS) { acc = 0; acc_phase ^= 1; }
           continue;
         }
       }
       wait_acc();
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
         if (splits > 1 && cluster_reduce) {
-          cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
+          cluster_splitk_park<Cfg>(taddr_acc, q, lane, smem_a);
           ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;
           continue;   // the reduction runs after the cluster barrier below
         }
         if (splits > 1) {
-          splitk_epilogue<Cfg>(taddr0, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
+          splitk_epilogue<Cfg>(taddr_acc, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
                                splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
-      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64) {
+      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && MR == 1) {
         if (sk_tiles > 0 && u.kb0 > 0) {   // stream-K: a later part of a tile's k-range, handed to the tile's owner
-          streamk_contribute<Cfg>(ew, taddr0, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
-          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          streamk_contribute<Cfg>(ew, taddr_acc, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
+          if (++acc == AS) { acc = 0; acc_phase ^= 1; }
           continue;
         }
       }
+#pragma unroll
+      for (int r = 0; r < MR; ++r) {   // the 128-row blocks of this CTA's tile, one accumulator each
+      const uint32_t taddr0 = taddr_acc + uint32_t(r * BN);
+      const int m0 = m_tile0 + r * kBlockM + q * 32;
       for (int j = j_begin; j < j_end; ++j) {
         uint32_t packed[EN / 2];
         if constexpr (Cfg::ACC_F32) {
@@ -715,18 +794,20 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == j_end - 1) release_tmem();
+        if (j == j_end - 1 && r == MR - 1) release_tmem();
         epilogue_store_chunk<Cfg>(packed, epi_buf, row_off, sw, lane, &tmap_c, n0 + j * EN, m0, M, N);
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      if (++acc == AS) { acc = 0; acc_phase ^= 1; }
     }
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
     if (lane == 0) tma_store_wait_read<0>();
+    B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) B200_TRACE(7);)
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
+  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
     if (splits > 1 && cluster_reduce) {
       __syncwarp();
       cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
@@ -741,6 +822,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   __syncwarp();   // single-lane roles rejoin their warp before the aligned barrier
   tc_fence_before_sync();
   if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
+  B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(8);)
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);

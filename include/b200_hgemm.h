@@ -47,6 +47,9 @@ int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group);
 /* TMA-multicast cluster shape of a configuration (1 x 1 = none): cluster_m x cluster_n single-CTA groups work on
  * adjacent tiles; A tiles are shared along N, B tiles along M. */
 int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n);
+/* 128-row blocks per CTA: 1, or 2 for the configurations whose CTAs own 256 rows (two MMAs per k-step that share the
+ * B tile in shared memory); the tile is then 128 * m_rep * cta_group rows. Negative status for an unknown id. */
+int b200_hgemm_config_m_rep(int config_id);
 /* The configuration the dispatcher uses for this problem (acc_bits = 32 or 16). */
 int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
 /* Same, also reporting the rasterisation group (0 = kernel default) and the split-K factor (1 = none).

@@ -32,7 +32,8 @@ def test_config_table_and_dispatch(built_libs):
     for c in cfgs:
         assert (c["bn"] == 32 or c["bn"] % 64 == 0) and c["bn"] <= 256 and c["cta_group"] in (1, 2) and c["stages"] >= 2
         assert c["cta_group"] * c["cluster_m"] * c["cluster_n"] <= 8
-        smem = 1024 + c["stages"] * (128 * 64 * 2 + (c["bn"] // c["cta_group"]) * 64 * 2) + 32768 + 256
+        assert c["m_rep"] in (1, 2)
+        smem = 1024 + c["stages"] * (128 * c["m_rep"] * 64 * 2 + (c["bn"] // c["cta_group"]) * 64 * 2) + 32768 + 256
         assert smem + 256 <= 232448
     ids = {c["id"] for c in cfgs}
     for acc in ("fp32", "fp16"):
@@ -93,7 +94,7 @@ def test_tuned_table_entries_are_launchable_for_every_grid_shape(built_libs):
             cid, gm, sp = capi.select(acc, m, n, k)
             c = cfgs[cid]
             assert 0 <= gm <= 64
-            assert -(-m // 128) >= c["cta_group"] * c["cluster_m"], (m, n, k, acc, c)
+            assert -(-m // 128) >= c["cta_group"] * c["cluster_m"] * c["m_rep"], (m, n, k, acc, c)
             assert -(-n // c["bn"]) >= c["cluster_n"], (m, n, k, acc, c)
             if sp != 1:
                 assert sp in (-2, -4, -8) or 2 <= sp <= 64
@@ -114,7 +115,7 @@ def test_off_grid_shapes_borrow_the_nearest_tuned_entry(built_libs):
 
 def _check_schedule(cfg, m, n, k, splits, num_sms=148):
     """Every k-block of every tile is run exactly once, and the stream-K fix-up protocol cannot wait forever."""
-    tile_m = 128 * cfg["cta_group"] * cfg["cluster_m"]
+    tile_m = 128 * cfg["cta_group"] * cfg["cluster_m"] * cfg["m_rep"]
     tile_n = cfg["bn"] * cfg["cluster_n"]
     tiles = -(-m // tile_m) * -(-n // tile_n)
     nkb = -(-k // 64)
