@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round 2, first GPU call: validate the stream-K branch (never run on a GPU before this script).
+# Round 2, first GPU call: validate the round-2 candidate branch (stream-K: exact in its first light, owner path
+# reworked since; config 26 = 512x256 pair tile: never run on a GPU before this script).
 #   1. regression ladder of the plain schedule (the loops were rewritten around WorkIter);
 #   2. stream-K exactness: every plain config x {tail, tail+wave} x shapes with 1..13 contributors per tile;
 #   3. A/B timings on the wave-quantised shapes that motivated it (tile count = 0.865 of a wave multiple);
@@ -14,7 +15,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $
 run() { timeout 120 $DC "$@" >> $LOG 2>&1; rc=$?; [ $rc -ne 0 ] && echo "  -> exit $rc : $*" >> $LOG; }
 echo "== 1. plain regression" >> $LOG
 for acc in 32 16; do
-  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20; do
+  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20 26; do
     run check $acc $cfg 1024 1536 1024
     run check $acc $cfg 1000 1000 1000
   done
@@ -49,6 +50,11 @@ ab 32 0 1024 1024 4096 0
 ab 32 4 1024 1024 4096 0
 ab 16 3 512 8192 8192 0
 ab 16 3 4096 4096 4096 8
+echo "== 3b. config 26 (512x256 pair tile, one accumulator stage) against config 3 on large shapes" >> $LOG
+for acc in 32 16; do run check $acc 26 4096 4096 4096 8; run check $acc 26 1000 1224 2048; run check $acc 26 8192 8192 8192 8; done
+for shape in "8192 8192 8192" "16384 16384 16384" "16384 16384 4096" "4096 12288 16384" "4096 4096 4096" "8192 8192 2048"; do
+  for cfg in 3 26; do run time 32 $cfg $shape 10 8 1; done
+done
 echo "== 4. pytest" >> $LOG
 timeout 1200 python -m pytest tests -m gpu -x -q >> $LOG 2>&1; echo "pytest rc=$?" >> $LOG
 grep -E "FAIL|exit|watchdog|TIME|pytest rc|passed|failed" $LOG | tail -60
