@@ -70,6 +70,9 @@ struct WorkIter {
     }
   }
 
+  // after next(): does this worker have another unit to run?
+  __host__ __device__ __forceinline__ bool has_more() const { return it < end || dp_tile < num_tiles; }
+
   __host__ __device__ __forceinline__ bool next(WorkUnit& u) {
     if (it < end) {
       u.tile = it / nkb;

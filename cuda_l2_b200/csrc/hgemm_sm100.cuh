@@ -113,6 +113,10 @@ struct Config {
   static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
+  // stream-K, owner unit that ends a worker's schedule: the partial tiles are fetched by bulk copies into the (then
+  // idle) pipeline shared memory, one region per epilogue warp holding a ring of chunk images
+  static constexpr int FIX_REGION_BYTES = ((STAGES * STAGE_BYTES) / 8) & ~1023;
+  static constexpr int FIX_BARS = 8 * 3;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static constexpr int ACC_COLS = M_REP * BN;                // TMEM columns of one accumulator stage
   static constexpr int ACC_STAGES = (kAccStages * ACC_COLS <= 512) ? kAccStages : 1;   // ring depth that fits TMEM
@@ -128,7 +132,7 @@ struct Config {
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
-  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");   // ACC_STAGES <= kAccStages
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 8 + 8 * FIX_BARS <= BAR_BYTES, "barrier block too small");   // ACC_STAGES <= kAccStages
 };
 
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
@@ -327,6 +331,7 @@ __device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int spli
 // warps stay as decoupled as in the plain epilogue and the flags are zero again when the grid ends.
 constexpr int kMaxStreamKSlots = 160;   // CTAs of a launch (>= 148 SMs), one partial-tile slot each
 constexpr int kStreamKFlagsPerSlot = 8; // epilogue warps
+constexpr bool kStreamKBulkFixup = true;   // false: always fetch the partials with register loads (streamk_own)
 
 template <class Cfg>
 struct StreamK {
@@ -335,6 +340,8 @@ struct StreamK {
   static constexpr int CHUNK_U4 = R4 * 32;                                  // one warp, one chunk
   static constexpr int SLOT_U4 = 4 * Cfg::EPI_CHUNKS * CHUNK_U4;            // one CTA: 128 rows x BN columns
   static constexpr size_t SLOT_BYTES = size_t(SLOT_U4) * 16;
+  static constexpr uint32_t CHUNK_BYTES = uint32_t(CHUNK_U4) * 16;
+  static constexpr int FIX_RING = Cfg::FIX_REGION_BYTES / int(CHUNK_BYTES) >= 3 ? 3 : Cfg::FIX_REGION_BYTES / int(CHUNK_BYTES);
 };
 
 // this warp's chunk `j` of the accumulator, raw: fp32 bit patterns, or fp16 pairs (two columns per register)
@@ -496,6 +503,107 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
     for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
 }
 
+// Owner whose unit ends the worker's schedule: nothing hides the fix-up any more, and register loads would crawl
+// (one 16-byte load per lane and round trip). The pipeline shared memory is idle once the own accumulator is
+// complete, so lane 0 streams this warp's chunk images of every contributor through a ring of bulk copies
+// (`fix_smem`: this warp's region, `fix_bar`: its FIX_RING mbarriers, phase 0 on entry) while the warp sums them from
+// shared memory — same order of additions as streamk_own, hence the same bits.
+template <class Cfg, class WaitAcc, class ReleaseTmem>
+__device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t taddr0, const uint4* __restrict__ ws,
+                                                 unsigned* __restrict__ flags, int slot0, int slot_stride, int n,
+                                                 const CUtensorMap* tmap_c, int m0, int n0, int M, int N,
+                                                 uint32_t fix_smem, uint32_t fix_bar, WaitAcc wait_acc,
+                                                 ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  constexpr int RING = SK::FIX_RING;
+  static_assert(RING >= 2, "the fix-up ring needs two chunk images per epilogue warp");
+  if (w.lane == 0) {
+    for (int p = 0; p < n; ++p) {
+      const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(f) == 0u) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { printf("b200_hgemm watchdog: stream-K slot %d never arrived\n", slot0 + p * slot_stride); __trap(); }
+      }
+    }
+  }
+  __syncwarp();
+  const int total = (w.j_end - w.j_begin) * n;   // items in (chunk, contributor) order
+  auto issue = [&](int i) {
+    if (w.lane == 0) {
+      const int jj = i / n, p = i - jj * n, s = i % RING;
+      const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 +
+                         size_t(w.q * Cfg::EPI_CHUNKS + w.j_begin + jj) * SK::CHUNK_U4;
+      mbar_arrive_expect_tx(fix_bar + 8 * s, SK::CHUNK_BYTES);
+      bulk_load_1d(fix_smem + uint32_t(s) * SK::CHUNK_BYTES, src, SK::CHUNK_BYTES, fix_bar + 8 * s);
+    }
+  };
+  wait_acc();                 // every MMA of the worker has read its operands: the pipeline shared memory is free
+  fence_proxy_async_all();    // the partials were written through the generic proxy (by other CTAs, acquired above)
+  for (int i = 0; i < RING && i < total; ++i) issue(i);
+  int item = 0;
+#pragma unroll 1
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    float f[Cfg::EPI_N];
+#pragma unroll
+    for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = 0.f;
+    for (int p = 0; p < n; ++p, ++item) {
+      const int s = item % RING;
+      mbar_wait(fix_bar + 8 * s, uint32_t(item / RING) & 1u);
+      const uint32_t img = fix_smem + uint32_t(s) * SK::CHUNK_BYTES + uint32_t(w.lane) * 16u;
+#pragma unroll
+      for (int i = 0; i < SK::R4; ++i) {
+        const uint4 v = ld_shared_v4(img + uint32_t(i) * 512u);
+        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if constexpr (Cfg::ACC_F32) {
+            f[4 * i + c] += __uint_as_float(x[c]);
+          } else {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&x[c]);
+            f[8 * i + 2 * c] += __low2float(hh);
+            f[8 * i + 2 * c + 1] += __high2float(hh);
+          }
+        }
+      }
+      __syncwarp();   // every lane is done with this ring slot
+      if (item + RING < total) {
+        fence_proxy_async_smem();
+        issue(item + RING);
+      }
+    }
+    uint32_t packed[Cfg::EPI_N / 2];
+    const bool last = (j == w.j_end - 1);
+    if constexpr (Cfg::ACC_F32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + j * Cfg::EPI_N + 32 * h, v);
+        tmem_ld_wait();
+        if (last && h == 1) release_tmem();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          packed[16 * h + i] = pack_f16x2_rn(f[32 * h + 2 * i] + __uint_as_float(v[2 * i]),
+                                             f[32 * h + 2 * i + 1] + __uint_as_float(v[2 * i + 1]));
+      }
+    } else {
+      uint32_t r[SK::REGS];
+      streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+      if (last) release_tmem();
+#pragma unroll
+      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+        const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
+        packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+      }
+    }
+    epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
+  }
+  __syncwarp();
+  if (w.lane == 0)
+    for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kNumThreads, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
@@ -532,6 +640,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const uint32_t bar_tmem_empty = bar_tmem_full + 8 * kAccStages;
   const uint32_t bar_splitk = bar_tmem_empty + 8 * kAccStages;   // split-K: bulk loads of the partial slices
   const uint32_t tmem_slot = bar_splitk + 8;
+  const uint32_t bar_fix = tmem_slot + 8;                        // [8 epilogue warps][3]: stream-K fix-up rings
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -568,6 +677,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
     mbar_init(bar_splitk, 1);
+    if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && Cfg::M_REP == 1) {
+      for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -741,8 +853,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && MR == 1) {
         if (sk_tiles > 0 && u.kb0 == 0 && u.kb1 < num_k_blocks) {   // stream-K: the head of a tile, which owns it
           const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
-          streamk_own<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m_tile0 + q * 32,
-                           n0, M, N, wait_acc, release_tmem);
+          if (kStreamKBulkFixup && !work.has_more())   // nothing left to hide the fix-up behind: stream it through shared memory
+            streamk_own_bulk<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c,
+                                  m_tile0 + q * 32, n0, M, N, smem_a + uint32_t(ew.ew) * Cfg::FIX_REGION_BYTES,
+                                  bar_fix + 8 * 3 * ew.ew, wait_acc, release_tmem);
+          else
+            streamk_own<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m_tile0 + q * 32,
+                             n0, M, N, wait_acc, release_tmem);
           if (++acc == AS) { acc = 0; acc_phase ^= 1; }
           continue;
         }
