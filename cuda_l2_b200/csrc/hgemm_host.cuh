@@ -69,9 +69,15 @@ inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int 
   cuuint32_t estr[2] = {1, 1};
   // the swizzle span equals the box's inner extent: 64 fp16 = 128 B, 32 fp16 = 64 B
   const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // experiment hook: B200_HGEMM_L2_PROMOTION = 0 (none) | 1 (64 B) | 2 (128 B) | 3 (256 B, the default)
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = std::getenv("B200_HGEMM_L2_PROMOTION");
+    const int v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? kOk : kEncodeFailed;
 }
 
