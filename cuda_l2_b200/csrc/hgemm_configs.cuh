@@ -2,7 +2,8 @@
 // generated per-shape translation units (kernels/b200_*/<M>_<N>_<K>.cu).
 //   X(id, BN, STAGES, CTA_GROUP, CLUSTER_M, CLUSTER_N, M_REP)
 // Stage counts fill the 227 KB of shared memory left after the 32 KB epilogue staging area.
-// M_REP = 2: 256 rows per CTA (two MMAs per k-step sharing the B tile): config 26 is a 512 x 256 tile per CTA pair.
+// M_REP = 2: 256 rows per CTA (two MMAs per k-step sharing the B tile): config 26 is a 512 x 256 tile per CTA pair,
+// 27 / 28 two such pairs sharing B / A by multicast (27 is the shape of cuBLAS's nvjet_hsh_256x256_64x4_2x1_2cta).
 // CLUSTER_M x CLUSTER_N > 1: TMA-multicast clusters of groups (single CTAs or CTA pairs): A shared along N, B along M.
 #pragma once
 #include "hgemm_host.cuh"
@@ -34,8 +35,10 @@
   X(23, 128, 8, 2, 2, 1, 1)      \
   X(24, 192, 6, 2, 1, 2, 1)      \
   X(25, 192, 6, 2, 2, 1, 1)     \
-  X(26, 256, 4, 2, 1, 1, 2)
+  X(26, 256, 4, 2, 1, 1, 2)      \
+  X(27, 256, 4, 2, 2, 1, 2)      \
+  X(28, 256, 4, 2, 1, 2, 2)
 
 namespace b200 {
-constexpr int kNumConfigs = 27;
+constexpr int kNumConfigs = 29;
 }

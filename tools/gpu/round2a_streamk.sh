@@ -15,7 +15,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $
 run() { timeout 120 $DC "$@" >> $LOG 2>&1; rc=$?; [ $rc -ne 0 ] && echo "  -> exit $rc : $*" >> $LOG; }
 echo "== 1. plain regression" >> $LOG
 for acc in 32 16; do
-  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20 26; do
+  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20 26 27 28; do
     run check $acc $cfg 1024 1536 1024
     run check $acc $cfg 1000 1000 1000
   done
@@ -53,7 +53,7 @@ ab 16 3 4096 4096 4096 8
 echo "== 3b. config 26 (512x256 pair tile, one accumulator stage) against config 3 on large shapes" >> $LOG
 for acc in 32 16; do run check $acc 26 4096 4096 4096 8; run check $acc 26 1000 1224 2048; run check $acc 26 8192 8192 8192 8; done
 for shape in "8192 8192 8192" "16384 16384 16384" "16384 16384 4096" "4096 12288 16384" "4096 4096 4096" "8192 8192 2048"; do
-  for cfg in 3 26; do run time 32 $cfg $shape 10 8 1; done
+  for cfg in 3 26 27 28; do run time 32 $cfg $shape 10 8 1; done
 done
 echo "== 4. pytest" >> $LOG
 timeout 1200 python -m pytest tests -m gpu -x -q >> $LOG 2>&1; echo "pytest rc=$?" >> $LOG
