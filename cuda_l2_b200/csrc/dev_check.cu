@@ -7,7 +7,7 @@
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
 //   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
-//   dev_check_trace trace <acc_bits> <cfg|-1> <M> <N> <K> [gm splits]   per-CTA phase timestamps of one launch (trace build only)
+//   dev_check_trace trace <acc_bits> <cfg|-1> <M> <N> <K> [gm splits cold]   per-CTA phase timestamps of one launch (trace build only)
 //   dev_check grid  <acc_bits> [part nparts budget_ms min_gflop max_gflop [wall]]  time every config on the whole shape grid (CSV);
 //                                                     "wall": rank by the harness metric instead of CUDA-event time
 //
@@ -462,10 +462,22 @@ extern "C" int b200_hgemm_trace_slots(void);
 extern "C" int b200_hgemm_trace_arm(int max_ctas);
 extern "C" int b200_hgemm_trace_read(unsigned long long* out, int ctas);
 
-static int do_trace(int acc, int cfg, int M, int N, int K, int gm, int splits) {
+// cold != 0: before the traced launch, other work (a cuBLAS GEMM on other operands, 512 MB of memset) evicts this
+// kernel's instructions, descriptors and operands from the caches and the TLBs — the state every call of the
+// harness's rotation starts from, as opposed to the back-to-back state of `dev_check time`.
+static int do_trace(int acc, int cfg, int M, int N, int K, int gm, int splits, int cold) {
   Problem p; alloc_random(p, M, N, K);
   for (int i = 0; i < 3; ++i) if (run_ours(acc, cfg, p, gm, splits)) { printf("TRACE launch failed\n"); return 1; }
   CK(cudaDeviceSynchronize());
+  if (cold) {
+    Problem other; alloc_random(other, 2048, 2048, 2048);
+    void* scratch; const size_t bytes = size_t(512) << 20;
+    CK(cudaMalloc(&scratch, bytes));
+    for (int i = 0; i < 2; ++i) { cublas_tn(other, other.Cref); CK(cudaMemsetAsync(scratch, i, bytes)); }
+    CK(cudaDeviceSynchronize());
+    cudaFree(scratch);
+    other.release();
+  }
   const int kMaxCtas = 320, S = b200_hgemm_trace_slots();
   if (b200_hgemm_trace_arm(kMaxCtas)) { printf("TRACE arm failed\n"); return 1; }
   if (run_ours(acc, cfg, p, gm, splits)) { printf("TRACE launch failed\n"); return 1; }
@@ -505,8 +517,8 @@ static int do_trace(int acc, int cfg, int M, int N, int K, int gm, int splits) {
     rows[10].v.push_back((gt(c, 8) - gt(c, 0)) * 1e-3);
   }
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
-  printf("TRACE acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ctas=%d  first entry -> last exit %.2f us\n", acc, cfg, sel, gm, splits,
-         M, N, K, ctas, (t_end - t0) * 1e-3);
+  printf("TRACE acc=%d cfg=%d(%d) gm=%d splits=%d %s %dx%dx%d  ctas=%d  first entry -> last exit %.2f us\n", acc, cfg, sel, gm, splits,
+         cold ? "COLD" : "warm", M, N, K, ctas, (t_end - t0) * 1e-3);
   for (auto& r : rows) {
     if (r.v.empty()) continue;
     std::sort(r.v.begin(), r.v.end());
@@ -650,7 +662,7 @@ int main(int argc, char** argv) {
 #ifdef B200_HGEMM_TRACE
   if (mode == "trace" && argc >= 7)
     return do_trace(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 0,
-                    argc > 8 ? atoi(argv[8]) : 1);
+                    argc > 8 ? atoi(argv[8]) : 1, argc > 9 ? atoi(argv[9]) : 0);
 #endif
   if (mode == "probe") { probe_cluster_addresses<<<4, 32>>>(); CK(cudaDeviceSynchronize()); return 0; }
   if (mode == "wall" && argc >= 6)

@@ -41,6 +41,12 @@ run $DT trace 32 3 8192 8192 8192 8 1
 run $DT trace 32 3 512 8192 8192 0 1
 run $DT trace 32 2 128 8192 16384 0 1
 run $DT trace 32 2 1024 1024 1024 0 1
+# the same launches from the state the harness's rotation leaves behind (caches and TLBs hold other kernels' data):
+# the skinny HBM-bound shapes lose 15-20 % between back-to-back and isolated timing, cuBLAS only 5 %
+run $DT trace 32 2 128 8192 16384 0 1 1
+run $DT trace 32 2 1024 1024 1024 0 1 1
+run $DT trace 32 6 4096 4096 4096 8 1 1
+run $DT trace 32 3 512 8192 8192 0 1 1
 kill $SMI
 echo "== 3. ncu (serialised, cold: compare shapes of the numbers)" >> $LOG
 M="gpu__time_duration.sum,sm__cycles_elapsed.avg.per_second,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__data_bank_conflicts_pipe_lsu.sum,smsp__inst_executed.sum,launch__grid_size,launch__cluster_size"
