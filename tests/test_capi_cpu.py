@@ -175,3 +175,18 @@ def test_stream_k_fills_the_partial_wave_and_balances_the_workers(built_libs):
     assert _check_schedule(cfgs[18], 512, 8192, 8192, capi.STREAMK_TAIL)["sk_tiles"] == 0
     assert _check_schedule(cfgs[12], 512, 8192, 8192, capi.STREAMK_TAIL)["sk_tiles"] == 0
     assert _check_schedule(cfgs[3], 512, 8192, 128, capi.STREAMK_TAIL)["sk_tiles"] == 0
+
+
+def test_schedule_is_a_partition_for_random_problems(built_libs):
+    """Randomised version of the coverage test: odd sizes, short and long K, restricted SM counts, every mode."""
+    import random
+    rng = random.Random(20260923)
+    cfgs = capi.configs()
+    modes = (1, 2, 3, 7, 32, -2, -4, -8, capi.STREAMK_TAIL, capi.STREAMK_TAIL_PLUS_WAVE)
+    for _ in range(400):
+        cfg = rng.choice(cfgs)
+        m = rng.choice((8, 64, 72, 128, 200, 256, 520, 1024, 3000, 4096, 10000))
+        n = rng.choice((8, 64, 136, 256, 328, 1000, 2048, 5000, 8192))
+        k = rng.choice((8, 64, 72, 256, 512, 1096, 4096, 16384, 30000))
+        num_sms = rng.choice((8, 36, 100, 132, 148, 160))
+        _check_schedule(cfg, m, n, k, rng.choice(modes), num_sms)
