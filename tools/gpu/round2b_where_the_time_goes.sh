@@ -41,6 +41,12 @@ run $DT trace 32 3 8192 8192 8192 8 1
 run $DT trace 32 3 512 8192 8192 0 1
 run $DT trace 32 2 128 8192 16384 0 1
 run $DT trace 32 2 1024 1024 1024 0 1
+# the K = 1024..2048 family (7-9 us kernels, won on only 24-33 % of the shapes, by 0.5-2 us): where do the fixed costs sit?
+run $DT trace 32 -1 256 2048 2048
+run $DT trace 32 -1 1024 1024 2048
+run $DT trace 32 -1 512 2048 1024
+run $DT trace 32 -1 4096 2048 1024
+run $DT trace 32 -1 256 2048 2048 0 1 1
 # the same launches from the state the harness's rotation leaves behind (caches and TLBs hold other kernels' data):
 # the skinny HBM-bound shapes lose 15-20 % between back-to-back and isolated timing, cuBLAS only 5 %
 run $DT trace 32 2 128 8192 16384 0 1 1
