@@ -109,6 +109,11 @@ def build_trace(verbose: bool = False, force: bool = False) -> Path:
     return build_variant("trace", ["B200_HGEMM_TRACE"], verbose, force)
 
 
+def build_early_tma(verbose: bool = False, force: bool = False) -> Path:
+    """First TMA ring issued before the set-up barrier (-DB200_HGEMM_EARLY_TMA=1): the fixed-cost experiment."""
+    return build_variant("early", ["B200_HGEMM_EARLY_TMA=1"], verbose, force)
+
+
 def build_wait_hint(ns: int = 2000, verbose: bool = False, force: bool = False) -> Path:
     """mbarrier.try_wait with a suspend-time hint (-DB200_HGEMM_WAIT_HINT_NS): the polling-power experiment."""
     return build_variant("hint", [f"B200_HGEMM_WAIT_HINT_NS={ns}"], verbose, force)

@@ -47,6 +47,9 @@ constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
 constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+#ifndef B200_HGEMM_EARLY_TMA
+#define B200_HGEMM_EARLY_TMA 0       // experiment: first loads before the set-up barrier (see the set-up block)
+#endif
 
 // Developer instrumentation (only in builds with -DB200_HGEMM_TRACE, i.e. libb200_hgemm_trace.so; the product build
 // contains none of it): per-CTA timestamps of the kernel's phases, read back by `dev_check_trace trace`.
@@ -678,12 +681,34 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
     mbar_init(bar_splitk, 1);
     if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && Cfg::M_REP == 1) {
-      for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
+      if (sk_tiles > 0)
+        for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
+#if B200_HGEMM_EARLY_TMA
+    // Experiment (default off): a CTA that shares its barriers with nobody need not wait for the set-up barrier (and
+    // the TMEM allocation behind it) before its first loads leave — the first ring of the first unit is issued here,
+    // by the thread that has just initialised the barriers; the producer loop below starts behind it.
+    if constexpr (Cfg::CLUSTER_CTAS == 1) {
+      WorkIter first_work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+      WorkUnit u0;
+      if (first_work.next(u0)) {
+        fence_proxy_async_smem();   // the initialised barriers (generic proxy) before the loads' complete_tx (async proxy)
+        const TileCoord tc = tile_coord(u0.tile, num_m_blocks, num_n_blocks, group_m);
+        const int npre = min(STAGES, u0.kb1 - u0.kb0);
+        for (int st = 0; st < npre; ++st) {
+          mbar_arrive_expect_tx(bar_full + 8 * st, Cfg::STAGE_BYTES);
+          tma_load_2d_hint<1>(smem_a + st * Cfg::A_STAGE_BYTES, &tmap_a, bar_full + 8 * st, (u0.kb0 + st) * kBlockK,
+                              tc.m_blk * Cfg::TILE_M, hint_a);
+          tma_load_2d_hint<1>(smem_b + st * Cfg::B_STAGE_BYTES, &tmap_b, bar_full + 8 * st, (u0.kb0 + st) * kBlockK,
+                              tc.n_blk * BN, hint_b);
+        }
+      }
+    }
+#endif
   }
   if (warp == 2) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
@@ -720,11 +745,24 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     B200_TRACE_ONLY(bool trace_first = true;)
     WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
     WorkUnit u;
+#if B200_HGEMM_EARLY_TMA
+    bool skip_issued = (Cfg::CLUSTER_CTAS == 1);   // the first ring of the first unit left during set-up
+#endif
     while (work.next(u)) {
       const TileCoord tc = tile_coord(u.tile, num_m_blocks, num_n_blocks, group_m);
       const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M + cn * Cfg::A_BOX_ROWS;
       const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
-      for (int kb = u.kb0; kb < u.kb1; ++kb) {
+      int kb_begin = u.kb0;
+#if B200_HGEMM_EARLY_TMA
+      if (skip_issued) {
+        const int npre = min(STAGES, u.kb1 - u.kb0);
+        kb_begin += npre;
+        stage = npre % STAGES;
+        phase = uint32_t(npre / STAGES);
+        skip_issued = false;
+      }
+#endif
+      for (int kb = kb_begin; kb < u.kb1; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
