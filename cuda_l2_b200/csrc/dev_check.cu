@@ -239,6 +239,12 @@ static int do_time(int acc, int cfg, int M, int N, int K, int iters, int gm = 0,
   float ours = time_ms([&] { run_ours(acc, cfg, p, gm, splits); }, iters);
   float blas = time_ms([&] { cublas_tn(p, p.Cref); }, iters);
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
+  // the same two, one launch at a time (event pair around each launch, median): what a caller that synchronises after
+  // every call can see, with the kernel's ramp-up and tail no longer hidden behind its neighbours
+  const float ours_iso = time_isolated_ms([&] { run_ours(acc, cfg, p, gm, splits); }, std::max(iters, 9));
+  const float blas_iso = time_isolated_ms([&] { cublas_tn(p, p.Cref); }, std::max(iters, 9));
+  printf("TIME-ISOLATED acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ours %.2f us | cublas %.2f us | ratio %.3f\n", acc, cfg, sel, gm,
+         splits, M, N, K, ours_iso * 1e3, blas_iso * 1e3, blas_iso / ours_iso);
   printf("TIME acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ours %.2f us %.1f TFLOP/s | cublas(fp32acc) %.2f us %.1f TFLOP/s | ratio %.3f\n",
          acc, cfg, sel, gm, splits, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
   p.release();
