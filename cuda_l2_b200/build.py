@@ -114,6 +114,11 @@ def build_early_tma(verbose: bool = False, force: bool = False) -> Path:
     return build_variant("early", ["B200_HGEMM_EARLY_TMA=1"], verbose, force)
 
 
+def build_split_setup(verbose: bool = False, force: bool = False) -> Path:
+    """TMEM allocation behind the first set-up barrier, producer not waiting for it (-DB200_HGEMM_SPLIT_SETUP=1)."""
+    return build_variant("split", ["B200_HGEMM_SPLIT_SETUP=1"], verbose, force)
+
+
 def build_wait_hint(ns: int = 2000, verbose: bool = False, force: bool = False) -> Path:
     """mbarrier.try_wait with a suspend-time hint (-DB200_HGEMM_WAIT_HINT_NS): the polling-power experiment."""
     return build_variant("hint", [f"B200_HGEMM_WAIT_HINT_NS={ns}"], verbose, force)

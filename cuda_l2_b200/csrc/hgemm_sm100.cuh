@@ -47,6 +47,9 @@ constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
 constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+#ifndef B200_HGEMM_SPLIT_SETUP
+#define B200_HGEMM_SPLIT_SETUP 0     // experiment: TMEM allocation after the barrier-publishing barrier, producer not waiting for it
+#endif
 #ifndef B200_HGEMM_EARLY_TMA
 #define B200_HGEMM_EARLY_TMA 0       // experiment: first loads before the set-up barrier (see the set-up block)
 #endif
@@ -710,6 +713,25 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
 #endif
   }
+#if B200_HGEMM_SPLIT_SETUP
+  // Experiment (default off): the barrier that publishes the initialised mbarriers comes first, the TMEM allocation
+  // after it, published by a second barrier that the producer warp does not take part in — its first loads are in
+  // flight while the allocator works.
+  __syncwarp();
+  if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
+  uint32_t tmem_base = 0;
+  if (warp != 0) {
+    if (warp == 2) {
+      tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish<CG>();
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    asm volatile("bar.sync 2, %0;" ::"n"(kNumThreads - 32) : "memory");
+    tc_fence_after_sync();
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  }
+#else
   if (warp == 2) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish<CG>();
@@ -720,6 +742,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+#endif
   B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
   int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
