@@ -436,7 +436,8 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
       }
       all.swap(keep);
       for (auto& cd : all) cd.t.clear();
-      for (int r = 0; r < iters + 1; ++r) {
+      const int rounds = est_ms < 0.03 ? 3 * iters : iters;   // host-clock samples of a 15 us call scatter by ~1 us: average more of them
+      for (int r = 0; r < rounds + 1; ++r) {
         // three library calls per round keep the mix (and the power state) close to the harness's rotation
         for (int rep = 0; rep < 3; ++rep) { const float tb = once_wall([&] { cublas_tn(p, p.Cref); }); if (r) blas_t.push_back(tb); }
         for (auto& cd : all) { const float t = once_wall([&] { run_ours(acc, cd.c, p, cd.gm, cd.sp); }); if (r) cd.t.push_back(t); }
