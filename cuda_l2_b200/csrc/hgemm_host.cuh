@@ -249,7 +249,7 @@ int max_resident_clusters(const DeviceInfo& di) {
   if (max_clusters_dev != di.dev) {
     cudaLaunchConfig_t probe{};
     probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
-    probe.blockDim = dim3(kNumThreads, 1, 1);
+    probe.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
     probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cudaLaunchAttribute pa[1];
     pa[0].id = cudaLaunchAttributeClusterDimension;
@@ -320,7 +320,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(plan.workers * (cluster_reduce || plan.splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
-  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -44,7 +44,8 @@ namespace b200 {
 constexpr int kBlockK = 64;          // 64 fp16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;           // K per tcgen05.mma.kind::f16
 constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
-constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
+constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant);
+                                     // 8 warps (256 threads) for tiles of one 64-column chunk, whose second epilogue set would idle
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
 #ifndef B200_HGEMM_SPLIT_SETUP
@@ -116,6 +117,7 @@ struct Config {
   // two epilogue warps per TMEM lane quadrant share a tile's column chunks when there are at least two of them
   static constexpr int EPI_GROUPS = EPI_CHUNKS >= 2 ? 2 : 1;
   static constexpr int EPI_CHUNKS_PER_GROUP = (EPI_CHUNKS + EPI_GROUPS - 1) / EPI_GROUPS;
+  static constexpr int NUM_THREADS = EPI_GROUPS == 2 ? kNumThreads : kNumThreads - 128;   // no warps that would only wait
   static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
@@ -611,7 +613,7 @@ __device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(Cfg::NUM_THREADS, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, B_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {EPI_N, 32}
@@ -727,7 +729,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     }
     __syncwarp();
     tc_fence_before_sync();
-    asm volatile("bar.sync 2, %0;" ::"n"(kNumThreads - 32) : "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(Cfg::NUM_THREADS - 32) : "memory");
     tc_fence_after_sync();
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   }
