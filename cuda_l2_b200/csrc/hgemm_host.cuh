@@ -207,7 +207,7 @@ Plan make_plan(int M, int N, int K, int workers_avail, int splits) {
   p.num_tiles = num_m_blocks * num_n_blocks;
   p.nkb = (K + kBlockK - 1) / kBlockK;
   p.workers = std::max(workers_avail, 1);
-  const bool plain = Cfg::MCAST_CTAS == 1 && Cfg::BN >= 64 && Cfg::M_REP == 1;   // the K-decompositions are wired for these
+  const bool plain = Cfg::STREAM_K;   // no multicast cluster, BN >= 64, 128 rows per CTA: the K-decompositions are wired for these
   int sk_mode = 0;
   if (splits == kStreamKTail || splits == kStreamKTailPlusWave) { sk_mode = splits; splits = 1; }
   if (!plain) splits = 1;

@@ -48,6 +48,9 @@ constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 
                                      // 8 warps (256 threads) for tiles of one 64-column chunk, whose second epilogue set would idle
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+#ifndef B200_HGEMM_NO_K_DECOMP
+#define B200_HGEMM_NO_K_DECOMP 0     // experiment: kernels without split-K / stream-K code
+#endif
 #ifndef B200_HGEMM_SPLIT_SETUP
 #define B200_HGEMM_SPLIT_SETUP 0     // experiment: TMEM allocation after the barrier-publishing barrier, producer not waiting for it
 #endif
@@ -118,6 +121,10 @@ struct Config {
   static constexpr int EPI_GROUPS = EPI_CHUNKS >= 2 ? 2 : 1;
   static constexpr int EPI_CHUNKS_PER_GROUP = (EPI_CHUNKS + EPI_GROUPS - 1) / EPI_GROUPS;
   static constexpr int NUM_THREADS = EPI_GROUPS == 2 ? kNumThreads : kNumThreads - 128;   // no warps that would only wait
+  // which K-decompositions this configuration's kernel carries (B200_HGEMM_NO_K_DECOMP: an experiment build without
+  // any of them, to see what their code costs the plain path)
+  static constexpr bool SPLIT_K = !B200_HGEMM_NO_K_DECOMP && CTA_GROUP_ * CLUSTER_M_ * CLUSTER_N_ == 1 && BN_ >= 64 && M_REP_ == 1;
+  static constexpr bool STREAM_K = !B200_HGEMM_NO_K_DECOMP && CLUSTER_M_ * CLUSTER_N_ == 1 && BN_ >= 64 && M_REP_ == 1;
   static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
@@ -685,7 +692,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
     mbar_init(bar_splitk, 1);
-    if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && Cfg::M_REP == 1) {
+    if constexpr (Cfg::STREAM_K) {
       if (sk_tiles > 0)
         for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
     }
@@ -892,7 +899,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
       const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M;
       const int n0 = (tc.n_blk * CN + cn) * BN;
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
+      if constexpr (Cfg::SPLIT_K) {
         if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
       const uint32_t taddr_acc = tmem_base + uint32_t(acc * Cfg::ACC_COLS) + (uint32_t(q * 32) << 16);
@@ -913,7 +920,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       };
       [[maybe_unused]] uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
       [[maybe_unused]] unsigned* sk_flags = splitk_ctr + 2 * kMaxSplitTiles;
-      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && MR == 1) {
+      if constexpr (Cfg::STREAM_K) {
         if (sk_tiles > 0 && u.kb0 == 0 && u.kb1 < num_k_blocks) {   // stream-K: the head of a tile, which owns it
           const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
           if (kStreamKBulkFixup && !work.has_more())   // nothing left to hide the fix-up behind: stream it through shared memory
@@ -928,7 +935,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         }
       }
       wait_acc();
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
+      if constexpr (Cfg::SPLIT_K) {
         if (splits > 1 && cluster_reduce) {
           cluster_splitk_park<Cfg>(taddr_acc, q, lane, smem_a);
           ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;
@@ -940,7 +947,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
         }
       }
-      if constexpr (Cfg::MCAST_CTAS == 1 && BN >= 64 && MR == 1) {
+      if constexpr (Cfg::STREAM_K) {
         if (sk_tiles > 0 && u.kb0 > 0) {   // stream-K: a later part of a tile's k-range, handed to the tile's owner
           streamk_contribute<Cfg>(ew, taddr_acc, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
           if (++acc == AS) { acc = 0; acc_phase ^= 1; }
@@ -987,7 +994,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64 && MR == 1) {
+  if constexpr (Cfg::SPLIT_K) {
     if (splits > 1 && cluster_reduce) {
       __syncwarp();
       cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
