@@ -436,7 +436,9 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
       }
       all.swap(keep);
       for (auto& cd : all) cd.t.clear();
-      const int rounds = est_ms < 0.03 ? 3 * iters : iters;   // host-clock samples of a 15 us call scatter by ~1 us: average more of them
+      int rounds = est_ms < 0.03 ? 3 * iters : iters;   // host-clock samples of a 15 us call scatter by ~1 us: average more of them
+      // and long kernels need the rotation to last: the power cap settles over tens of milliseconds (aim at >= 0.3 s)
+      rounds = std::max(rounds, std::min(40, int(300.0 / (13.0 * est_ms))));
       for (int r = 0; r < rounds + 1; ++r) {
         // three library calls per round keep the mix (and the power state) close to the harness's rotation
         for (int rep = 0; rep < 3; ++rep) { const float tb = once_wall([&] { cublas_tn(p, p.Cref); }); if (r) blas_t.push_back(tb); }
