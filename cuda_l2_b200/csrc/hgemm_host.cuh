@@ -265,9 +265,55 @@ int max_resident_clusters(const DeviceInfo& di) {
   return max_clusters;
 }
 
-// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". splits > 1 requests
-// split-K (clamped to what the problem allows; only for CTA_GROUP == 1 configurations).
-template <class Cfg>
+// One (configuration, K-mode) instance of the kernel: opt into its dynamic shared memory once, then launch.
+// Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this template
+// (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be merged across
+// them (STB_GNU_UNIQUE) while each object still launches its own kernel copy. Key on both.
+struct LaunchArgs {
+  CUtensorMap ma, mb, mc;
+  int M, N, K, group_m;
+  Plan plan;
+  float* ws; unsigned* ctr; __half* c;
+  uint64_t hint_a, hint_b;
+  cudaStream_t stream;
+};
+
+template <class Cfg, int KMODE>
+int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
+  static thread_local int attr_dev = -1;
+  static thread_local const void* attr_fn = nullptr;
+  const void* this_fn = reinterpret_cast<const void*>(&hgemm_tn_kernel<Cfg, KMODE>);
+  if (attr_dev != di.dev || attr_fn != this_fn) {
+    cudaError_t e = cudaFuncSetAttribute(hgemm_tn_kernel<Cfg, KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return int(e);
+    attr_dev = di.dev;
+    attr_fn = this_fn;
+  }
+  constexpr bool kSplit = (KMODE == kWorkspaceSplitK || KMODE == kClusterSplitK);
+  const int cluster = (KMODE == kClusterSplitK) ? a.plan.cluster_reduce : Cfg::CLUSTER_CTAS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(a.plan.workers * (kSplit ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);   // split-K: one CTA per (tile, split)
+  cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg, KMODE>, a.ma, a.mb, a.mc, a.M, a.N, a.K, a.group_m,
+                                     a.plan.splits, a.plan.sk_tiles, a.ws, a.ctr, a.c, a.hint_a, a.hint_b);
+  return e == cudaSuccess ? kOk : int(e);
+}
+
+// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". `splits`: 1 none, > 1 workspace
+// split-K, -2/-4/-8 cluster split-K, kStreamKTail / kStreamKTailPlusWave stream-K — each clamped to what the problem and
+// the configuration allow. MODES: bit mask of the K-modes this call site may need (a per-shape translation unit
+// names its one mode and so compiles two kernels instead of four; the plain mode is always available as fallback).
+template <class Cfg, unsigned MODES = 0xFu>
 int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStream_t stream,
            int group_m = 0, int max_ctas = 0, int splits = 1) {
   int st = validate(A, Bt, C, M, N, K);
@@ -275,74 +321,60 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   const DeviceInfo& di = device_info();
   if (di.cc_major != 10) return kNotBlackwell;
 
-  // Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this
-  // template (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be
-  // merged across them (STB_GNU_UNIQUE) while each object still launches its own kernel copy. Key on both.
-  static thread_local int attr_dev = -1;
-  static thread_local const void* attr_fn = nullptr;
-  const void* this_fn = reinterpret_cast<const void*>(&hgemm_tn_kernel<Cfg>);
-  if (attr_dev != di.dev || attr_fn != this_fn) {
-    cudaError_t e = cudaFuncSetAttribute(hgemm_tn_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return int(e);
-    attr_dev = di.dev;
-    attr_fn = this_fn;
-  }
-
-  CUtensorMap ma, mb, mc;
+  LaunchArgs a{};
   MapCache& cache = map_cache();
-  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &ma)) != kOk) return st;
-  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &mb)) != kOk) return st;
-  if ((st = cache.get(C, M, N, 32, &mc, Cfg::EPI_N)) != kOk) return st;
+  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &a.ma)) != kOk) return st;
+  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &a.mb)) != kOk) return st;
+  if ((st = cache.get(C, M, N, 32, &a.mc, Cfg::EPI_N)) != kOk) return st;
+
+  constexpr bool kCanSplit = Cfg::SPLIT_K && (MODES & ((1u << kWorkspaceSplitK) | (1u << kClusterSplitK)));
+  constexpr bool kCanStream = Cfg::STREAM_K && (MODES & (1u << kStreamK));
+  const bool wants_stream_k = (splits == kStreamKTail || splits == kStreamKTailPlusWave);
+  if ((wants_stream_k && !kCanStream) || (!wants_stream_k && splits != 1 && !kCanSplit)) splits = 1;
+  if (splits > 1 && !(MODES & (1u << kWorkspaceSplitK))) splits = 1;
+  if (splits < -1 && !(MODES & (1u << kClusterSplitK))) splits = 1;
 
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CLUSTER_CTAS;
   // Clusters must fit inside a GPC, so fewer than SMs / cluster size may be resident at once. Larger clusters are
   // always sized to what fits; CTA pairs only when stream-K is requested, whose owners wait for contributors
   // that must therefore be running (for the plain schedule a pair that starts late is merely late).
-  const bool wants_stream_k = (splits == kStreamKTail || splits == kStreamKTailPlusWave);
-  if (Cfg::CLUSTER_CTAS > 2 || (Cfg::CLUSTER_CTAS == 2 && wants_stream_k)) {
+  if (Cfg::CLUSTER_CTAS > 2 || (Cfg::CLUSTER_CTAS == 2 && wants_stream_k && splits != 1)) {
     workers = std::min(workers, max_resident_clusters<Cfg>(di));
   }
-  Plan plan = make_plan<Cfg>(M, N, K, workers, splits);
-  float* ws = nullptr;
-  unsigned* ctr = nullptr;
-  if ((plan.splits > 1 && !plan.cluster_reduce) || plan.sk_tiles) {
+  a.plan = make_plan<Cfg>(M, N, K, workers, splits);
+  if ((a.plan.splits > 1 && !a.plan.cluster_reduce) || a.plan.sk_tiles) {
     SplitKScratch* sk = nullptr;
     if (splitk_scratch(di.dev, stream, &sk) == kOk) {
-      ws = sk->ws; ctr = sk->ctr;
+      a.ws = sk->ws; a.ctr = sk->ctr;
     } else {
       cudaGetLastError();
-      plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed / more than 8 streams): run undivided
+      a.plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed / more than 8 streams): run undivided
     }
   }
-  const int cluster_reduce = plan.cluster_reduce;
-  if (group_m <= 0) group_m = (Cfg::CTA_GROUP == 2) ? 8 : 16;
-
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(plan.workers * (cluster_reduce || plan.splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
-  cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_reduce ? cluster_reduce : Cfg::CLUSTER_CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (Cfg::CLUSTER_CTAS > 1 || cluster_reduce) ? 1 : 0;
+  a.M = M; a.N = N; a.K = K;
+  a.group_m = group_m > 0 ? group_m : (Cfg::CTA_GROUP == 2 ? 8 : 16);
+  a.c = static_cast<__half*>(C);
+  a.stream = stream;
   // L2 eviction priorities: when one operand is streamed (about) once while the other is re-read by every tile row
   // or column and is small enough to live in L2, keep the small one and let the streamed one go first.
-  uint64_t hint_a = ptx::kL2EvictNormal, hint_b = ptx::kL2EvictNormal;
+  a.hint_a = ptx::kL2EvictNormal; a.hint_b = ptx::kL2EvictNormal;
   if (cache_hints_enabled()) {
     const size_t a_bytes = size_t(M) * K * 2, b_bytes = size_t(N) * K * 2;
     const int n_tiles = (N + Cfg::BN - 1) / Cfg::BN, m_tiles = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     constexpr size_t kL2Keep = size_t(48) << 20, kStream = size_t(96) << 20;
-    if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { hint_a = ptx::kL2EvictFirst; hint_b = ptx::kL2EvictLast; }
-    else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { hint_b = ptx::kL2EvictFirst; hint_a = ptx::kL2EvictLast; }
+    if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { a.hint_a = ptx::kL2EvictFirst; a.hint_b = ptx::kL2EvictLast; }
+    else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { a.hint_b = ptx::kL2EvictFirst; a.hint_a = ptx::kL2EvictLast; }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, plan.splits, cluster_reduce ? 1 : 0, plan.sk_tiles, ws, ctr,
-                                     static_cast<__half*>(C), hint_a, hint_b);
-  return e == cudaSuccess ? kOk : int(e);
+  if constexpr (kCanStream) {
+    if (a.plan.sk_tiles > 0) return launch_mode<Cfg, kStreamK>(di, a);
+  }
+  if constexpr (Cfg::SPLIT_K && (MODES & (1u << kClusterSplitK))) {
+    if (a.plan.cluster_reduce) return launch_mode<Cfg, kClusterSplitK>(di, a);
+  }
+  if constexpr (Cfg::SPLIT_K && (MODES & (1u << kWorkspaceSplitK))) {
+    if (a.plan.splits > 1) return launch_mode<Cfg, kWorkspaceSplitK>(di, a);
+  }
+  return launch_mode<Cfg, kPlain>(di, a);
 }
 
 }  // namespace host

@@ -48,6 +48,10 @@ constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 
                                      // 8 warps (256 threads) for tiles of one 64-column chunk, whose second epilogue set would idle
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+// How a launch divides K. The kernel is compiled once per (configuration, mode), so that the plain schedule — nearly
+// every launch — carries none of the three other epilogues: a quarter of the instructions, and registers to spare.
+enum KMode : int { kPlain = 0, kWorkspaceSplitK = 1, kClusterSplitK = 2, kStreamK = 3 };
+
 #ifndef B200_HGEMM_NO_K_DECOMP
 #define B200_HGEMM_NO_K_DECOMP 0     // experiment: kernels without split-K / stream-K code
 #endif
@@ -619,15 +623,14 @@ __device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t
     for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
 }
 
-template <class Cfg>
+template <class Cfg, int KMODE = kPlain>
 __global__ void __launch_bounds__(Cfg::NUM_THREADS, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, B_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {EPI_N, 32}
                 int M, int N, int K, int group_m,
-                int splits,                       // split-K factor; > 1 only with CLUSTER_CTAS == 1, one unit per CTA
-                int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
-                int sk_tiles,                     // stream-K: the first sk_tiles tiles are cut along K across all workers (0 = off)
+                int splits_arg,                   // split-K factor (modes kWorkspaceSplitK / kClusterSplitK: one unit per CTA)
+                int sk_tiles_arg,                 // mode kStreamK: the first sk_tiles tiles are cut along K across all workers
                 float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K) / stream-K slots
                 unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] split-K arrive / done counters, then the
                                                      // stream-K flags; all zero between launches
@@ -641,6 +644,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   constexpr bool kMcast = Cfg::MCAST_CTAS > 1;
   constexpr int AS = Cfg::ACC_STAGES;
   constexpr int MR = Cfg::M_REP;
+  constexpr bool kSplit = (KMODE == kWorkspaceSplitK || KMODE == kClusterSplitK);
+  static_assert(!kSplit || Cfg::SPLIT_K, "this configuration has no split-K epilogues");
+  static_assert(KMODE != kStreamK || Cfg::STREAM_K, "this configuration has no stream-K epilogues");
+  // the schedule parameters a mode does not use are constants for it
+  const int splits = kSplit ? splits_arg : 1;
+  const int sk_tiles = (KMODE == kStreamK) ? sk_tiles_arg : 0;
   using namespace ptx;
 
   extern __shared__ uint8_t smem_raw[];
@@ -692,9 +701,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
     mbar_init(bar_splitk, 1);
-    if constexpr (Cfg::STREAM_K) {
-      if (sk_tiles > 0)
-        for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
+    if constexpr (KMODE == kStreamK) {
+      for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
@@ -754,7 +762,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #endif
   B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
-  int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
+  [[maybe_unused]] int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
@@ -899,8 +907,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
       const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M;
       const int n0 = (tc.n_blk * CN + cn) * BN;
-      if constexpr (Cfg::SPLIT_K) {
-        if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
+      if constexpr (kSplit) {
+        if (eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
       const uint32_t taddr_acc = tmem_base + uint32_t(acc * Cfg::ACC_COLS) + (uint32_t(q * 32) << 16);
       // the MMA warp's commit: this unit's accumulator is complete
@@ -920,8 +928,8 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       };
       [[maybe_unused]] uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
       [[maybe_unused]] unsigned* sk_flags = splitk_ctr + 2 * kMaxSplitTiles;
-      if constexpr (Cfg::STREAM_K) {
-        if (sk_tiles > 0 && u.kb0 == 0 && u.kb1 < num_k_blocks) {   // stream-K: the head of a tile, which owns it
+      if constexpr (KMODE == kStreamK) {
+        if (u.kb0 == 0 && u.kb1 < num_k_blocks) {   // the head of a tile, which owns it
           const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
           if (kStreamKBulkFixup && !work.has_more())   // nothing left to hide the fix-up behind: stream it through shared memory
             streamk_own_bulk<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c,
@@ -935,20 +943,16 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
         }
       }
       wait_acc();
-      if constexpr (Cfg::SPLIT_K) {
-        if (splits > 1 && cluster_reduce) {
-          cluster_splitk_park<Cfg>(taddr_acc, q, lane, smem_a);
-          ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;
-          continue;   // the reduction runs after the cluster barrier below
-        }
-        if (splits > 1) {
-          splitk_epilogue<Cfg>(taddr_acc, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
-                               splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
-          continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
-        }
-      }
-      if constexpr (Cfg::STREAM_K) {
-        if (sk_tiles > 0 && u.kb0 > 0) {   // stream-K: a later part of a tile's k-range, handed to the tile's owner
+      // (split-K modes: one unit per CTA, so no accumulator ring bookkeeping is needed after it)
+      if constexpr (KMODE == kClusterSplitK) {
+        cluster_splitk_park<Cfg>(taddr_acc, q, lane, smem_a);
+        ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;   // the reduction runs after the cluster barrier below
+      } else if constexpr (KMODE == kWorkspaceSplitK) {
+        splitk_epilogue<Cfg>(taddr_acc, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
+                             splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
+      } else {
+      if constexpr (KMODE == kStreamK) {
+        if (u.kb0 > 0) {   // a later part of a tile's k-range, handed to the tile's owner
           streamk_contribute<Cfg>(ew, taddr_acc, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
           if (++acc == AS) { acc = 0; acc_phase ^= 1; }
           continue;
@@ -986,6 +990,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       }
       }
       if (++acc == AS) { acc = 0; acc_phase ^= 1; }
+      }   // plain / stream-K modes
     }
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
@@ -994,15 +999,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (Cfg::SPLIT_K) {
-    if (splits > 1 && cluster_reduce) {
-      __syncwarp();
-      cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
-      if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4)
-        cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
-      __syncwarp();
-      cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
-    }
+  if constexpr (KMODE == kClusterSplitK) {
+    __syncwarp();
+    cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4)
+      cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
+    __syncwarp();
+    cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
   }
 
   // ------------------------------------------------------------------ teardown
