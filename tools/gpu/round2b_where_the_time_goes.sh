@@ -9,7 +9,7 @@ cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 LOG=gpurun_out/round2b.log
 : > $LOG
-python -c "from cuda_l2_b200 import build; build.build_trace(); build.build_wait_hint(2000); build.build_early_tma(); build.build_split_setup(); build.build_no_k_decomp()" >> $LOG 2>&1
+python -c "from cuda_l2_b200 import build; build.build_trace(); build.build_wait_hint(2000); build.build_early_tma(); build.build_split_setup()" >> $LOG 2>&1
 DC=cuda_l2_b200/lib/dev_check
 DT=cuda_l2_b200/lib/dev_check_trace
 nvidia-smi --query-gpu=timestamp,clocks.sm,clocks.mem,power.draw,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown \
@@ -66,12 +66,6 @@ for spec in "2 1024 1024 2048 0" "4 256 2048 2048 0" "3 4096 2048 1024 8" "6 409
   set -- $spec
   run $DS check 32 $1 $2 $3 $4 $5
   run $DC time 32 $1 $2 $3 $4 200 $5; run $DS time 32 $1 $2 $3 $4 200 $5
-done
-echo "== 2d. kernels without split-K / stream-K code (dev_check_plain: half the instructions): cold-start cost of code size" >> $LOG
-DP=cuda_l2_b200/lib/dev_check_plain
-for spec in "2 1024 1024 2048 0" "4 256 2048 2048 0" "1 512 2048 1024 0" "3 4096 2048 1024 8" "2 256 256 1024 0"; do
-  set -- $spec
-  run $DC time 32 $1 $2 $3 $4 200 $5; run $DP time 32 $1 $2 $3 $4 200 $5
 done
 kill $SMI
 echo "== 3. ncu (serialised, cold: compare shapes of the numbers)" >> $LOG
