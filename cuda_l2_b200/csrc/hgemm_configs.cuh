@@ -4,6 +4,7 @@
 // Stage counts fill the 227 KB of shared memory left after the 32 KB epilogue staging area.
 // M_REP = 2: 256 rows per CTA (two MMAs per k-step sharing the B tile): config 26 is a 512 x 256 tile per CTA pair,
 // 27 / 28 two such pairs sharing B / A by multicast (27 is the shape of cuBLAS's nvjet_hsh_256x256_64x4_2x1_2cta).
+// 29 / 30: four CTA pairs in a 2 x 2 multicast cluster (8 CTAs: both operands fetched from L2 once per two pairs).
 // CLUSTER_M x CLUSTER_N > 1: TMA-multicast clusters of groups (single CTAs or CTA pairs): A shared along N, B along M.
 #pragma once
 #include "hgemm_host.cuh"
@@ -37,8 +38,10 @@
   X(25, 192, 6, 2, 2, 1, 1)     \
   X(26, 256, 4, 2, 1, 1, 2)      \
   X(27, 256, 4, 2, 2, 1, 2)      \
-  X(28, 256, 4, 2, 1, 2, 2)
+  X(28, 256, 4, 2, 1, 2, 2)      \
+  X(29, 256, 6, 2, 2, 2, 1)      \
+  X(30, 128, 8, 2, 2, 2, 1)
 
 namespace b200 {
-constexpr int kNumConfigs = 29;
+constexpr int kNumConfigs = 31;
 }

@@ -15,7 +15,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $
 run() { timeout 120 $DC "$@" >> $LOG 2>&1; rc=$?; [ $rc -ne 0 ] && echo "  -> exit $rc : $*" >> $LOG; }
 echo "== 1. plain regression" >> $LOG
 for acc in 32 16; do
-  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20 26 27 28; do
+  for cfg in 0 1 2 3 4 5 6 12 10 18 19 20 26 27 28 29 30; do
     run check $acc $cfg 1024 1536 1024
     run check $acc $cfg 1000 1000 1000
   done
