@@ -96,7 +96,9 @@ def test_tuned_table_entries_are_launchable_for_every_grid_shape(built_libs):
             assert 0 <= gm <= 64
             assert -(-m // 128) >= c["cta_group"] * c["cluster_m"] * c["m_rep"], (m, n, k, acc, c)
             assert -(-n // c["bn"]) >= c["cluster_n"], (m, n, k, acc, c)
-            if sp != 1:
+            if sp in (capi.STREAMK_TAIL, capi.STREAMK_TAIL_PLUS_WAVE):   # stream-K: single CTAs and CTA pairs
+                assert c["cluster_m"] * c["cluster_n"] == 1 and c["bn"] >= 64 and c["m_rep"] == 1, (m, n, k, acc, sp, c)
+            elif sp != 1:
                 assert sp in (-2, -4, -8) or 2 <= sp <= 64
                 assert c["cta_group"] == 1 and c["cluster_m"] * c["cluster_n"] == 1 and c["bn"] >= 64, (m, n, k, acc, sp, c)
                 seen_cluster_split += sp < 0
