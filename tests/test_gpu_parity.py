@@ -217,12 +217,20 @@ def test_size_independent_properties_at_full_size(acc):
 
 
 def test_host_buffer_entry_point_round_trips():
-    m, n, k = 512, 768, 256
-    a = torch.from_numpy(oracle.fill_zero_one((m, k), 2, 5)).pin_memory()
-    bt = torch.from_numpy(oracle.fill_zero_one((n, k), 2, 6)).pin_memory()
-    c = torch.empty((m, n), dtype=torch.half).pin_memory()
-    capi.hgemm_host(a, bt.reshape(k, n), c, "fp32")
-    assert np.array_equal(c.numpy(), oracle.hgemm_f32acc(a.numpy(), bt.numpy(), fast=True))
+    # small: one copy in, one GEMM, one copy out; large: B first, then A / GEMM / C in four pipelined row blocks
+    # (ragged M: the last block is shorter), from pinned and from pageable memory, twice (streams and events are reused)
+    for (m, n, k), acc in (((512, 768, 256), "fp32"), ((4096, 2048, 1024), "fp32"), ((3000, 1224, 2048), "fp16")):
+        a_np, bt_np = oracle.fill_zero_one((m, k), 3, 5), oracle.fill_zero_one((n, k), 3, 6)
+        want = oracle.hgemm_f32acc(a_np, bt_np, fast=True)
+        for pinned in (True, False):
+            a, bt = torch.from_numpy(a_np.copy()), torch.from_numpy(bt_np.copy())
+            c = torch.full((m, n), float("nan"), dtype=torch.half)
+            if pinned:
+                a, bt, c = a.pin_memory(), bt.pin_memory(), c.pin_memory()
+            for _ in range(2):
+                c.fill_(float("nan"))
+                capi.hgemm_host(a, bt.reshape(k, n), c, acc)
+                assert np.array_equal(c.numpy(), want), (m, n, k, acc, pinned)
 
 
 def test_errors_are_loud():
