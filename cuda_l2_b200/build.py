@@ -84,23 +84,49 @@ def build_dev_check(verbose: bool = False, force: bool = False) -> Path:
     return out
 
 
-def build_trace(verbose: bool = False, force: bool = False) -> Path:
-    """Developer build with per-CTA phase timestamps (-DB200_HGEMM_TRACE): libb200_hgemm_trace.so + dev_check_trace.
+def build_variant(name: str, defines: list[str], verbose: bool = False, force: bool = False) -> Path:
+    """Developer build of the library and of dev_check with extra -D flags: libb200_hgemm_<name>.so + dev_check_<name>.
 
-    Not part of build_all(): the product library contains no instrumentation."""
+    Not part of build_all(): the product library is always the plain build."""
     LIB_DIR.mkdir(exist_ok=True)
     build_baselines(verbose, force)
-    lib = LIB_DIR / "libb200_hgemm_trace.so"
+    flags = [f"-D{d}" for d in defines]
+    lib = LIB_DIR / f"libb200_hgemm_{name}.so"
     src = CSRC / "b200_hgemm_capi.cu"
     if force or _stale(lib, [src] + _headers()):
-        _run([nvcc_path(), *ARCH_FLAGS, *COMMON, "-DB200_HGEMM_TRACE", "--shared", "-o", str(lib), str(src)], verbose)
-    out = LIB_DIR / "dev_check_trace"
+        _run([nvcc_path(), *ARCH_FLAGS, *COMMON, *flags, "--shared", "-o", str(lib), str(src)], verbose)
+    out = LIB_DIR / f"dev_check_{name}"
     dsrc = CSRC / "dev_check.cu"
     if force or _stale(out, [dsrc, lib] + _headers()):
-        _run([nvcc_path(), *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", "-DB200_HGEMM_TRACE", "-o", str(out), str(dsrc),
-              f"-L{LIB_DIR}", "-lb200_hgemm_trace", "-lb200_baselines", "-lcublas", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"],
+        _run([nvcc_path(), *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", *flags, "-o", str(out), str(dsrc),
+              f"-L{LIB_DIR}", f"-lb200_hgemm_{name}", "-lb200_baselines", "-lcublas", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"],
              verbose)
     return out
+
+
+def build_trace(verbose: bool = False, force: bool = False) -> Path:
+    """Per-CTA phase timestamps (-DB200_HGEMM_TRACE): libb200_hgemm_trace.so + dev_check_trace."""
+    return build_variant("trace", ["B200_HGEMM_TRACE"], verbose, force)
+
+
+def build_early_tma(verbose: bool = False, force: bool = False) -> Path:
+    """First TMA ring issued before the set-up barrier (-DB200_HGEMM_EARLY_TMA=1): the fixed-cost experiment."""
+    return build_variant("early", ["B200_HGEMM_EARLY_TMA=1"], verbose, force)
+
+
+def build_split_setup(verbose: bool = False, force: bool = False) -> Path:
+    """TMEM allocation behind the first set-up barrier, producer not waiting for it (-DB200_HGEMM_SPLIT_SETUP=1)."""
+    return build_variant("split", ["B200_HGEMM_SPLIT_SETUP=1"], verbose, force)
+
+
+def build_no_k_decomp(verbose: bool = False, force: bool = False) -> Path:
+    """Kernels without split-K / stream-K code (-DB200_HGEMM_NO_K_DECOMP=1): what does that code cost the plain path?"""
+    return build_variant("plain", ["B200_HGEMM_NO_K_DECOMP=1"], verbose, force)
+
+
+def build_wait_hint(ns: int = 2000, verbose: bool = False, force: bool = False) -> Path:
+    """mbarrier.try_wait with a suspend-time hint (-DB200_HGEMM_WAIT_HINT_NS): the polling-power experiment."""
+    return build_variant("hint", [f"B200_HGEMM_WAIT_HINT_NS={ns}"], verbose, force)
 
 
 def build_all(verbose: bool = False, force: bool = False) -> dict[str, Path]:

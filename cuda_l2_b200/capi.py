@@ -42,10 +42,14 @@ def hgemm_lib() -> ctypes.CDLL:
         lib.b200_hgemm_num_configs.restype = i
         lib.b200_hgemm_config_info.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_config_cluster.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i)]
+        lib.b200_hgemm_config_m_rep.argtypes = [i]
         lib.b200_hgemm_select_config.argtypes = [i, i, i, i]
         lib.b200_hgemm_select.argtypes = [i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_run_config.argtypes = [i, i, vp, vp, vp, i, i, i, i, i, i, vp]
         lib.b200_hgemm_host.argtypes = [i, vp, vp, vp, i, i, i]
+        ip = ctypes.POINTER(i)
+        lib.b200_hgemm_schedule_units.argtypes = [i, i, i, i, i, i, i, ip, i, ip, ip, ip]
+        lib.b200_hgemm_schedule_units.restype = i
         lib.b200_hgemm_launch_count.restype = ctypes.c_ulonglong
         lib.b200_hgemm_strerror.argtypes = [i]
         lib.b200_hgemm_strerror.restype = ctypes.c_char_p
@@ -74,9 +78,9 @@ def exported_symbols() -> dict[str, list[str]]:
     return {
         "libb200_hgemm.so": [
             "b200_hgemm_f32acc", "b200_hgemm_f16acc", "b200_hgemm_num_configs", "b200_hgemm_config_info",
-            "b200_hgemm_config_cluster",
+            "b200_hgemm_config_cluster", "b200_hgemm_config_m_rep",
             "b200_hgemm_select_config", "b200_hgemm_select", "b200_hgemm_run_config", "b200_hgemm_host", "b200_hgemm_launch_count",
-            "b200_hgemm_strerror",
+            "b200_hgemm_strerror", "b200_hgemm_schedule_units",
         ],
         "libb200_baselines.so": [
             "b200_bl_init", "b200_bl_destroy", "b200_bl_cublas", "b200_bl_lt_heuristic", "b200_bl_lt_autotune_find",
@@ -148,7 +152,7 @@ def configs() -> list[dict]:
         cm, cn = ctypes.c_int(), ctypes.c_int()
         lib.b200_hgemm_config_cluster(cid, ctypes.byref(cm), ctypes.byref(cn))
         out.append({"id": cid, "bn": bn.value, "stages": st.value, "cta_group": cg.value,
-                    "cluster_m": cm.value, "cluster_n": cn.value})
+                    "cluster_m": cm.value, "cluster_n": cn.value, "m_rep": lib.b200_hgemm_config_m_rep(cid)})
     return out
 
 
@@ -162,6 +166,32 @@ def select(acc: str | int, m: int, n: int, k: int) -> tuple[int, int, int]:
     _check(hgemm_lib().b200_hgemm_select(ACC_BITS[acc], m, n, k, ctypes.byref(cid), ctypes.byref(gm), ctypes.byref(sp)),
            "b200_hgemm_select")
     return cid.value, gm.value, sp.value
+
+
+STREAMK_TAIL, STREAMK_TAIL_PLUS_WAVE = 100, 101      # `splits` codes of b200_hgemm_run_config
+
+
+def schedule(config_id: int, m: int, n: int, k: int, splits: int = 1, num_sms: int = 148) -> dict:
+    """Host-side view of the kernel's schedule (no GPU needed; the kernel walks the same code).
+
+    Returns ``{"workers": W, "sk_tiles": S, "units": [[(tile, kb0, kb1, contributors), ...] per worker]}``."""
+    lib = hgemm_lib()
+    nw, sk = ctypes.c_int(), ctypes.c_int()
+    cap = 64
+    buf, contrib = (ctypes.c_int * (3 * cap))(), (ctypes.c_int * cap)()
+    st = lib.b200_hgemm_schedule_units(config_id, m, n, k, splits, num_sms, 0, buf, cap, ctypes.byref(nw),
+                                       ctypes.byref(sk), contrib)
+    _check(min(st, 0), "b200_hgemm_schedule_units")
+    units = []
+    for w in range(nw.value):
+        cnt = lib.b200_hgemm_schedule_units(config_id, m, n, k, splits, num_sms, w, buf, cap, None, None, contrib)
+        _check(min(cnt, 0), "b200_hgemm_schedule_units")
+        if cnt > cap:
+            cap = cnt
+            buf, contrib = (ctypes.c_int * (3 * cap))(), (ctypes.c_int * cap)()
+            cnt = lib.b200_hgemm_schedule_units(config_id, m, n, k, splits, num_sms, w, buf, cap, None, None, contrib)
+        units.append([(buf[3 * j], buf[3 * j + 1], buf[3 * j + 2], contrib[j]) for j in range(cnt)])
+    return {"workers": nw.value, "sk_tiles": sk.value, "units": units}
 
 
 def launch_count() -> int:

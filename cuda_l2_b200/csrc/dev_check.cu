@@ -1,7 +1,8 @@
 // dev_check — standalone bring-up / tuning tool for libb200_hgemm.so (developer tool, not product).
 //
 //   dev_check check <acc_bits> <cfg|-1> <M> <N> <K> [gm splits]   exactness vs an independent GPU checker
-//   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters]  CUDA-event timing (+ cuBLAS for scale)
+//                                                     (splits: 1 none, >1 workspace, -2/-4/-8 cluster, 100/101 stream-K)
+//   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters gm splits]  CUDA-event timing (+ cuBLAS for scale)
 //   dev_check sustain <acc_bits> <cfg|-1> <M> <N> <K> [seconds gm splits]   burst vs power-capped throughput, ours and cuBLAS
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
 //   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
@@ -145,7 +146,7 @@ static int do_check(int acc, int cfg, int M, int N, int K, int gm = 0, int split
   p.reset_c();
   CK(cudaDeviceSynchronize());
   int st = run_ours(acc, cfg, p, gm, splits);
-  if (splits > 1 && st == 0) st = run_ours(acc, cfg, p, gm, splits);   // twice: the counters must reset themselves
+  if (splits != 1 && st == 0) st = run_ours(acc, cfg, p, gm, splits);   // twice: the counters / flags must reset themselves
   cudaError_t e = cudaDeviceSynchronize();
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
   if (st != 0 || e != cudaSuccess) {
@@ -229,17 +230,23 @@ static void alloc_random(Problem& p, int M, int N, int K) {
   CK(cudaDeviceSynchronize());
 }
 
-static int do_time(int acc, int cfg, int M, int N, int K, int iters) {
+static int do_time(int acc, int cfg, int M, int N, int K, int iters, int gm = 0, int splits = 1) {
   Problem p; alloc_random(p, M, N, K);
   const double flops = 2.0 * M * N * K;
-  int st = run_ours(acc, cfg, p);
+  int st = run_ours(acc, cfg, p, gm, splits);
   cudaError_t e = cudaDeviceSynchronize();
   if (st != 0 || e != cudaSuccess) { printf("TIME launch fail %d %s\n", st, cudaGetErrorString(e)); return 1; }
-  float ours = time_ms([&] { run_ours(acc, cfg, p); }, iters);
+  float ours = time_ms([&] { run_ours(acc, cfg, p, gm, splits); }, iters);
   float blas = time_ms([&] { cublas_tn(p, p.Cref); }, iters);
   int sel = cfg < 0 ? b200_hgemm_select_config(acc, M, N, K) : cfg;
-  printf("TIME acc=%d cfg=%d(%d) %dx%dx%d  ours %.2f us %.1f TFLOP/s | cublas(fp32acc) %.2f us %.1f TFLOP/s | ratio %.3f\n",
-         acc, cfg, sel, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
+  // the same two, one launch at a time (event pair around each launch, median): what a caller that synchronises after
+  // every call can see, with the kernel's ramp-up and tail no longer hidden behind its neighbours
+  const float ours_iso = time_isolated_ms([&] { run_ours(acc, cfg, p, gm, splits); }, std::max(iters, 9));
+  const float blas_iso = time_isolated_ms([&] { cublas_tn(p, p.Cref); }, std::max(iters, 9));
+  printf("TIME-ISOLATED acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ours %.2f us | cublas %.2f us | ratio %.3f\n", acc, cfg, sel, gm,
+         splits, M, N, K, ours_iso * 1e3, blas_iso * 1e3, blas_iso / ours_iso);
+  printf("TIME acc=%d cfg=%d(%d) gm=%d splits=%d %dx%dx%d  ours %.2f us %.1f TFLOP/s | cublas(fp32acc) %.2f us %.1f TFLOP/s | ratio %.3f\n",
+         acc, cfg, sel, gm, splits, M, N, K, ours * 1e3, flops / ours * 1e-9, blas * 1e3, flops / blas * 1e-9, blas / ours);
   p.release();
   fflush(stdout);
   return 0;
@@ -293,9 +300,10 @@ static int do_sweep(int acc, int M, int N, int K, int iters) {
   const int gms[] = {1, 2, 4, 8, 16, 32};
   for (int c = 0; c < ncfg; ++c) {
     int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
-    if ((M + 127) / 128 < cg * cm || (N + bn - 1) / bn < cn) continue;
+    const int mr = b200_hgemm_config_m_rep(c);
+    if ((M + 127) / 128 < cg * cm * mr || (N + bn - 1) / bn < cn) continue;
     for (int gm : gms) {
-      const int nm = (M + 128 * cg * cm - 1) / (128 * cg * cm);
+      const int nm = (M + 128 * cg * cm * mr - 1) / (128 * cg * cm * mr);
       if (gm > 1 && gm / 2 >= nm) continue;   // wider than the problem: same schedule as the previous one
       int st = run_ours(acc, c, p, gm);
       cudaError_t e = cudaDeviceSynchronize();
@@ -345,12 +353,14 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     std::vector<Cand> all;
     for (int c = 0; c < ncfg; ++c) {
       int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
-      if ((p.M + 127) / 128 < cg * cm || (p.N + bn - 1) / bn < cn) continue;   // part of the cluster would only see padding
+      const int mr = b200_hgemm_config_m_rep(c);
+      if ((p.M + 127) / 128 < cg * cm * mr || (p.N + bn - 1) / bn < cn) continue;   // part of the tile would only see padding
+      if (mr > 1 && p.K < 2048) continue;   // no accumulator ring: the epilogue is exposed, only a long K amortises it
       // pair + multicast: exact, but slower than plain pairs in every event-time run; the wall-metric mode keeps them,
       // because they move the fewest bytes per FLOP (what cuBLAS's 2x2_2cta kernels do) and that is what counts at the power cap
       if (cg == 2 && cm * cn > 1 && !wall_metric) continue;
-      const bool plain = (cm * cn == 1) && bn >= 64;
-      const int nm = (p.M + 128 * cg * cm - 1) / (128 * cg * cm);
+      const bool plain = (cm * cn == 1) && bn >= 64 && mr == 1;
+      const int nm = (p.M + 128 * cg * cm * mr - 1) / (128 * cg * cm * mr);
       const int nn = (p.N + bn * cn - 1) / (bn * cn);
       std::vector<std::pair<int, int>> cands = {{0, 1}};   // (group_m, splits)
       if (nm * nn > 148 / (cg * cm * cn) && nm > 1 && nn > 1) {
@@ -364,6 +374,17 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
       if (plain && cg == 1 && nkb >= 8 && nm * nn <= 148)
         for (int cs : {2, 4, 8})
           if (nm * nn * cs <= 296 && nkb >= 2 * cs) cands.push_back({0, -cs});   // cluster (DSMEM) split-K
+      // stream-K (splits code 100: the partial last wave, 101: that plus one full wave) where the tile count leaves
+      // more than 5 % of the last wave empty
+      const int workers = 148 / cg;
+      if (plain && (nm * nn) % workers != 0 && nkb >= 8 &&
+          double(nm * nn) / (double((nm * nn + workers - 1) / workers) * workers) < 0.95) {
+        const std::vector<int> sk_gms = (nm * nn > workers && nm > 1 && nn > 1) ? std::vector<int>{4, 16} : std::vector<int>{0};
+        for (int g : sk_gms) {
+          cands.push_back({g, 100});
+          if (nm * nn > workers) cands.push_back({g, 101});
+        }
+      }
       for (const auto& cand_ : cands) {
         const int gm = cand_.first, sp = cand_.second;
         if (gm > 1 && gm / 2 >= nm) continue;
@@ -647,7 +668,8 @@ int main(int argc, char** argv) {
     return do_check(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 0,
                     argc > 8 ? atoi(argv[8]) : 1);
   if (mode == "time" && argc >= 7)
-    return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20);
+    return do_time(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 20,
+                   argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 1);
   if (mode == "sustain" && argc >= 7)
     return do_sustain(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc > 7 ? atof(argv[7]) : 3.0,
                       argc > 8 ? atoi(argv[8]) : 0, argc > 9 ? atoi(argv[9]) : 1);

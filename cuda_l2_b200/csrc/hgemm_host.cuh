@@ -69,9 +69,15 @@ inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int 
   cuuint32_t estr[2] = {1, 1};
   // the swizzle span equals the box's inner extent: 64 fp16 = 128 B, 32 fp16 = 64 B
   const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // experiment hook: B200_HGEMM_L2_PROMOTION = 0 (none) | 1 (64 B) | 2 (128 B) | 3 (256 B, the default)
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = std::getenv("B200_HGEMM_L2_PROMOTION");
+    const int v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? kOk : kEncodeFailed;
 }
 
@@ -142,7 +148,9 @@ inline int validate(const void* A, const void* Bt, const void* C, int M, int N, 
 struct SplitKScratch {
   int dev = -1; cudaStream_t stream = nullptr; float* ws = nullptr; unsigned* ctr = nullptr;
 };
-constexpr size_t kSplitKWsBytes = size_t(160) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
+constexpr size_t kSplitKWsBytes = size_t(kMaxStreamKSlots) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
+// split-K arrive/done counters, then one stream-K flag per (CTA slot, epilogue warp)
+constexpr size_t kSplitKCtrBytes = (2 * kMaxSplitTiles + kMaxStreamKSlots * kStreamKFlagsPerSlot) * sizeof(unsigned);
 inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
   static thread_local SplitKScratch pool[8];
   SplitKScratch* free_slot = nullptr;
@@ -153,9 +161,9 @@ inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
   if (!free_slot) return kBadConfig;
   cudaError_t err = cudaMalloc(&free_slot->ws, kSplitKWsBytes);
   if (err != cudaSuccess) return int(err);
-  err = cudaMalloc(&free_slot->ctr, 2 * kMaxSplitTiles * sizeof(unsigned));
+  err = cudaMalloc(&free_slot->ctr, kSplitKCtrBytes);
   if (err != cudaSuccess) { cudaFree(free_slot->ws); free_slot->ws = nullptr; return int(err); }
-  err = cudaMemsetAsync(free_slot->ctr, 0, 2 * kMaxSplitTiles * sizeof(unsigned), stream);
+  err = cudaMemsetAsync(free_slot->ctr, 0, kSplitKCtrBytes, stream);
   if (err != cudaSuccess) return int(err);
   free_slot->dev = dev; free_slot->stream = stream;
   *out = free_slot;
@@ -167,7 +175,7 @@ inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
 template <class Cfg>
 int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   if (splits <= 1 || Cfg::CTA_GROUP != 1) return 1;
-  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + Cfg::BN - 1) / Cfg::BN);   // CTA_GROUP == 1: callers exclude M_REP > 1
   const int nkb = (K + kBlockK - 1) / kBlockK;
   if (tiles > kMaxSplitTiles) return 1;
   splits = std::min(splits, std::min(num_sms / tiles, std::min(nkb, 32)));   // <= 32: the slices of all partials must fit the pipeline smem
@@ -176,14 +184,136 @@ int clamp_splits(int splits, int M, int N, int K, int num_sms) {
   return std::max(splits, 1);
 }
 
+// `splits` values with a special meaning (besides > 1: workspace split-K, -2/-4/-8: cluster split-K)
+constexpr int kStreamKTail = 100;           // stream-K over the tiles of the partial last wave
+constexpr int kStreamKTailPlusWave = 101;   // ... plus one full wave, so that every worker's slice is longer than a tile
+constexpr int kMinStreamKSlice = 4;         // k-blocks; shorter slices are all pipeline fill and fix-up
+
+// What a launch will run: how many workers (CTAs, CTA pairs or clusters), which K-decomposition.
+struct Plan {
+  int num_tiles, nkb;
+  int workers;          // grid = workers * (CTAs per worker)
+  int splits;           // > 1: split-K, one worker per (tile, split)
+  int cluster_reduce;   // != 0: the splits of a tile form a cluster of this many CTAs and reduce through DSMEM
+  int sk_tiles;         // > 0: stream-K over the first sk_tiles tiles
+};
+
+// `workers_avail`: workers the device can hold at once (SMs / CTAs per worker, after max_ctas and cluster occupancy).
+template <class Cfg>
+Plan make_plan(int M, int N, int K, int workers_avail, int splits) {
+  Plan p{};
+  const int num_m_blocks = (M + Cfg::TILE_M * Cfg::CLUSTER_M - 1) / (Cfg::TILE_M * Cfg::CLUSTER_M);
+  const int num_n_blocks = (N + Cfg::BN * Cfg::CLUSTER_N - 1) / (Cfg::BN * Cfg::CLUSTER_N);
+  p.num_tiles = num_m_blocks * num_n_blocks;
+  p.nkb = (K + kBlockK - 1) / kBlockK;
+  p.workers = std::max(workers_avail, 1);
+  const bool plain = Cfg::STREAM_K;   // no multicast cluster, BN >= 64, 128 rows per CTA: the K-decompositions are wired for these
+  int sk_mode = 0;
+  if (splits == kStreamKTail || splits == kStreamKTailPlusWave) { sk_mode = splits; splits = 1; }
+  if (!plain) splits = 1;
+  if (splits < -1) {
+    int cs = -splits;
+    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8)) {
+      // every CTA of the cluster must own at least one k-block: halve the cluster until no k-range is empty
+      while (cs > 1 && (cs - 1) * ((p.nkb + cs - 1) / cs) >= p.nkb) cs /= 2;
+      if (cs > 1) p.cluster_reduce = cs;
+    }
+    splits = 1;
+  }
+  p.splits = clamp_splits<Cfg>(splits, M, N, K, p.workers);
+  if (p.cluster_reduce) {
+    p.workers = p.num_tiles * p.cluster_reduce;   // one cluster per tile, one CTA per k-range
+    p.splits = p.cluster_reduce;
+  } else if (p.splits > 1) {
+    p.workers = p.num_tiles * p.splits;           // exactly one CTA per (tile, split) unit
+  } else {
+    if (sk_mode && plain && p.num_tiles % p.workers != 0 && p.workers * Cfg::CTA_GROUP <= kMaxStreamKSlots) {
+      int sk = p.num_tiles % p.workers;
+      if (sk_mode == kStreamKTailPlusWave && p.num_tiles > p.workers) sk += p.workers;
+      if (sk * p.nkb / p.workers >= kMinStreamKSlice) p.sk_tiles = sk;
+    }
+    if (!p.sk_tiles && p.workers > p.num_tiles) p.workers = p.num_tiles;
+  }
+  return p;
+}
+
 inline bool cache_hints_enabled() {
   static const bool on = [] { const char* e = std::getenv("B200_HGEMM_NO_CACHE_HINTS"); return !(e && e[0] == '1'); }();
   return on;
 }
 
-// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". splits > 1 requests
-// split-K (clamped to what the problem allows; only for CTA_GROUP == 1 configurations).
+// How many clusters of this configuration the device holds at once (asked once per device).
 template <class Cfg>
+int max_resident_clusters(const DeviceInfo& di) {
+  static thread_local int max_clusters = 0, max_clusters_dev = -1;
+  if (max_clusters_dev != di.dev) {
+    cudaLaunchConfig_t probe{};
+    probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
+    probe.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
+    probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = Cfg::CLUSTER_CTAS; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+    probe.attrs = pa; probe.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, hgemm_tn_kernel<Cfg>, &probe) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = std::max(1, di.num_sms / Cfg::CLUSTER_CTAS * 7 / 8);
+    }
+    max_clusters = n; max_clusters_dev = di.dev;
+  }
+  return max_clusters;
+}
+
+// One (configuration, K-mode) instance of the kernel: opt into its dynamic shared memory once, then launch.
+// Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this template
+// (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be merged across
+// them (STB_GNU_UNIQUE) while each object still launches its own kernel copy. Key on both.
+struct LaunchArgs {
+  CUtensorMap ma, mb, mc;
+  int M, N, K, group_m;
+  Plan plan;
+  float* ws; unsigned* ctr; __half* c;
+  uint64_t hint_a, hint_b;
+  cudaStream_t stream;
+};
+
+template <class Cfg, int KMODE>
+int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
+  static thread_local int attr_dev = -1;
+  static thread_local const void* attr_fn = nullptr;
+  const void* this_fn = reinterpret_cast<const void*>(&hgemm_tn_kernel<Cfg, KMODE>);
+  if (attr_dev != di.dev || attr_fn != this_fn) {
+    cudaError_t e = cudaFuncSetAttribute(hgemm_tn_kernel<Cfg, KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return int(e);
+    attr_dev = di.dev;
+    attr_fn = this_fn;
+  }
+  constexpr bool kSplit = (KMODE == kWorkspaceSplitK || KMODE == kClusterSplitK);
+  const int cluster = (KMODE == kClusterSplitK) ? a.plan.cluster_reduce : Cfg::CLUSTER_CTAS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(a.plan.workers * (kSplit ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);   // split-K: one CTA per (tile, split)
+  cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg, KMODE>, a.ma, a.mb, a.mc, a.M, a.N, a.K, a.group_m,
+                                     a.plan.splits, a.plan.sk_tiles, a.ws, a.ctr, a.c, a.hint_a, a.hint_b);
+  return e == cudaSuccess ? kOk : int(e);
+}
+
+// group_m <= 0 selects the default rasterisation width. max_ctas <= 0 means "all SMs". `splits`: 1 none, > 1 workspace
+// split-K, -2/-4/-8 cluster split-K, kStreamKTail / kStreamKTailPlusWave stream-K — each clamped to what the problem and
+// the configuration allow. MODES: bit mask of the K-modes this call site may need (a per-shape translation unit
+// names its one mode and so compiles two kernels instead of four; the plain mode is always available as fallback).
+template <class Cfg, unsigned MODES = 0xFu>
 int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStream_t stream,
            int group_m = 0, int max_ctas = 0, int splits = 1) {
   int st = validate(A, Bt, C, M, N, K);
@@ -191,112 +321,60 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
   const DeviceInfo& di = device_info();
   if (di.cc_major != 10) return kNotBlackwell;
 
-  // Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this
-  // template (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be
-  // merged across them (STB_GNU_UNIQUE) while each object still launches its own kernel copy. Key on both.
-  static thread_local int attr_dev = -1;
-  static thread_local const void* attr_fn = nullptr;
-  const void* this_fn = reinterpret_cast<const void*>(&hgemm_tn_kernel<Cfg>);
-  if (attr_dev != di.dev || attr_fn != this_fn) {
-    cudaError_t e = cudaFuncSetAttribute(hgemm_tn_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return int(e);
-    attr_dev = di.dev;
-    attr_fn = this_fn;
-  }
-
-  CUtensorMap ma, mb, mc;
+  LaunchArgs a{};
   MapCache& cache = map_cache();
-  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &ma)) != kOk) return st;
-  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &mb)) != kOk) return st;
-  if ((st = cache.get(C, M, N, 32, &mc, Cfg::EPI_N)) != kOk) return st;
+  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &a.ma)) != kOk) return st;
+  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &a.mb)) != kOk) return st;
+  if ((st = cache.get(C, M, N, 32, &a.mc, Cfg::EPI_N)) != kOk) return st;
 
-  // schedule granularity: cluster blocks of (CLUSTER_M x TILE_M) x (CLUSTER_N x BN); 1 x 1 for plain configs
-  const int num_m_blocks = (M + Cfg::TILE_M * Cfg::CLUSTER_M - 1) / (Cfg::TILE_M * Cfg::CLUSTER_M);
-  const int num_n_blocks = (N + Cfg::BN * Cfg::CLUSTER_N - 1) / (Cfg::BN * Cfg::CLUSTER_N);
-  const int num_tiles = num_m_blocks * num_n_blocks;
+  constexpr bool kCanSplit = Cfg::SPLIT_K && (MODES & ((1u << kWorkspaceSplitK) | (1u << kClusterSplitK)));
+  constexpr bool kCanStream = Cfg::STREAM_K && (MODES & (1u << kStreamK));
+  const bool wants_stream_k = (splits == kStreamKTail || splits == kStreamKTailPlusWave);
+  if ((wants_stream_k && !kCanStream) || (!wants_stream_k && splits != 1 && !kCanSplit)) splits = 1;
+  if (splits > 1 && !(MODES & (1u << kWorkspaceSplitK))) splits = 1;
+  if (splits < -1 && !(MODES & (1u << kClusterSplitK))) splits = 1;
+
   int workers = (max_ctas > 0 ? max_ctas : di.num_sms) / Cfg::CLUSTER_CTAS;
-  if constexpr (Cfg::CLUSTER_CTAS > 2) {
-    // clusters must fit inside a GPC: ask the runtime how many can be resident at once (cached per device)
-    static thread_local int max_clusters = 0, max_clusters_dev = -1;
-    if (max_clusters_dev != di.dev) {
-      cudaLaunchConfig_t probe{};
-      probe.gridDim = dim3(unsigned(di.num_sms / Cfg::CLUSTER_CTAS * Cfg::CLUSTER_CTAS), 1, 1);
-      probe.blockDim = dim3(kNumThreads, 1, 1);
-      probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
-      cudaLaunchAttribute pa[1];
-      pa[0].id = cudaLaunchAttributeClusterDimension;
-      pa[0].val.clusterDim.x = Cfg::CLUSTER_CTAS; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
-      probe.attrs = pa; probe.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, hgemm_tn_kernel<Cfg>, &probe) != cudaSuccess || n < 1) {
-        cudaGetLastError();
-        n = std::max(1, di.num_sms / Cfg::CLUSTER_CTAS * 7 / 8);
-      }
-      max_clusters = n; max_clusters_dev = di.dev;
-    }
-    if (max_ctas <= 0 || workers > max_clusters) workers = std::min(workers, max_clusters);
+  // Clusters must fit inside a GPC, so fewer than SMs / cluster size may be resident at once. Larger clusters are
+  // always sized to what fits; CTA pairs only when stream-K is requested, whose owners wait for contributors
+  // that must therefore be running (for the plain schedule a pair that starts late is merely late).
+  if (Cfg::CLUSTER_CTAS > 2 || (Cfg::CLUSTER_CTAS == 2 && wants_stream_k && splits != 1)) {
+    workers = std::min(workers, max_resident_clusters<Cfg>(di));
   }
-  if (workers < 1) workers = 1;
-  if (Cfg::MCAST_CTAS > 1 || Cfg::BN < 64) splits = 1;   // split-K is wired for plain configs with BN >= 64
-  // splits < -1: split-K inside a thread-block cluster of |splits| CTAs (2, 4 or 8), reduced through DSMEM
-  int cluster_reduce = 0;
-  if (splits < -1) {
-    int cs = -splits;
-    const int nkb = (K + kBlockK - 1) / kBlockK;
-    if (Cfg::CTA_GROUP == 1 && (cs == 2 || cs == 4 || cs == 8)) {
-      // every CTA of the cluster must own at least one k-block: halve the cluster until no k-range is empty
-      while (cs > 1 && (cs - 1) * ((nkb + cs - 1) / cs) >= nkb) cs /= 2;
-      if (cs > 1) cluster_reduce = cs;
-    }
-    splits = 1;
-  }
-  splits = clamp_splits<Cfg>(splits, M, N, K, workers);
-  float* ws = nullptr;
-  unsigned* ctr = nullptr;
-  if (cluster_reduce) {
-    workers = num_tiles * cluster_reduce;   // one cluster per tile, one CTA per k-range
-    splits = cluster_reduce;
-  } else if (splits > 1) {
+  a.plan = make_plan<Cfg>(M, N, K, workers, splits);
+  if ((a.plan.splits > 1 && !a.plan.cluster_reduce) || a.plan.sk_tiles) {
     SplitKScratch* sk = nullptr;
     if (splitk_scratch(di.dev, stream, &sk) == kOk) {
-      ws = sk->ws; ctr = sk->ctr;
-      workers = num_tiles * splits;        // exactly one CTA per (tile, split) unit
+      a.ws = sk->ws; a.ctr = sk->ctr;
     } else {
       cudaGetLastError();
-      splits = 1;                          // no scratch (allocation failed / more than 8 streams): run unsplit
-      if (workers > num_tiles) workers = num_tiles;
+      a.plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed / more than 8 streams): run undivided
     }
-  } else if (workers > num_tiles) {
-    workers = num_tiles;
   }
-  if (group_m <= 0) group_m = (Cfg::CTA_GROUP == 2) ? 8 : 16;
-
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(workers * (cluster_reduce || splits > 1 ? 1 : Cfg::CLUSTER_CTAS)), 1, 1);
-  cfg.blockDim = dim3(kNumThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_reduce ? cluster_reduce : Cfg::CLUSTER_CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (Cfg::CLUSTER_CTAS > 1 || cluster_reduce) ? 1 : 0;
+  a.M = M; a.N = N; a.K = K;
+  a.group_m = group_m > 0 ? group_m : (Cfg::CTA_GROUP == 2 ? 8 : 16);
+  a.c = static_cast<__half*>(C);
+  a.stream = stream;
   // L2 eviction priorities: when one operand is streamed (about) once while the other is re-read by every tile row
   // or column and is small enough to live in L2, keep the small one and let the streamed one go first.
-  uint64_t hint_a = ptx::kL2EvictNormal, hint_b = ptx::kL2EvictNormal;
+  a.hint_a = ptx::kL2EvictNormal; a.hint_b = ptx::kL2EvictNormal;
   if (cache_hints_enabled()) {
     const size_t a_bytes = size_t(M) * K * 2, b_bytes = size_t(N) * K * 2;
     const int n_tiles = (N + Cfg::BN - 1) / Cfg::BN, m_tiles = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     constexpr size_t kL2Keep = size_t(48) << 20, kStream = size_t(96) << 20;
-    if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { hint_a = ptx::kL2EvictFirst; hint_b = ptx::kL2EvictLast; }
-    else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { hint_b = ptx::kL2EvictFirst; hint_a = ptx::kL2EvictLast; }
+    if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { a.hint_a = ptx::kL2EvictFirst; a.hint_b = ptx::kL2EvictLast; }
+    else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { a.hint_b = ptx::kL2EvictFirst; a.hint_a = ptx::kL2EvictLast; }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg>, ma, mb, mc, M, N, K, group_m, splits, cluster_reduce ? 1 : 0, ws, ctr,
-                                     static_cast<__half*>(C), hint_a, hint_b);
-  return e == cudaSuccess ? kOk : int(e);
+  if constexpr (kCanStream) {
+    if (a.plan.sk_tiles > 0) return launch_mode<Cfg, kStreamK>(di, a);
+  }
+  if constexpr (Cfg::SPLIT_K && (MODES & (1u << kClusterSplitK))) {
+    if (a.plan.cluster_reduce) return launch_mode<Cfg, kClusterSplitK>(di, a);
+  }
+  if constexpr (Cfg::SPLIT_K && (MODES & (1u << kWorkspaceSplitK))) {
+    if (a.plan.splits > 1) return launch_mode<Cfg, kWorkspaceSplitK>(di, a);
+  }
+  return launch_mode<Cfg, kPlain>(di, a);
 }
 
 }  // namespace host

@@ -26,12 +26,16 @@
 //     a tcgen05.commit multicast to every CTA of the consumer's cluster row and column;
 //   * split-K for problems with few output tiles and long K, two flavours, both deterministic: partial tiles
 //     through an fp32 global workspace with a distributed reduction (up to 32 splits), or the splits of a tile
-//     form a cluster and reduce through distributed shared memory (2/4/8 splits, no workspace).
+//     form a cluster and reduce through distributed shared memory (2/4/8 splits, no workspace);
+//   * stream-K for tile counts that leave the last wave partly empty: the first tiles of the schedule are cut along
+//     K into one equal slice per worker (hgemm_schedule.cuh), the partial sums of a tile meet in its owner's
+//     epilogue through the same workspace, in fixed k order.
 #pragma once
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "hgemm_schedule.cuh"
 #include "ptx_sm100.cuh"
 
 
@@ -40,9 +44,23 @@ namespace b200 {
 constexpr int kBlockK = 64;          // 64 fp16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;           // K per tcgen05.mma.kind::f16
 constexpr int kBlockM = 128;         // rows per CTA (all 128 TMEM lanes)
-constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
+constexpr int kNumThreads = 384;     // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two per TMEM lane quadrant);
+                                     // 8 warps (256 threads) for tiles of one 64-column chunk, whose second epilogue set would idle
 constexpr int kEpiWarp0 = 4;
 constexpr int kAccStages = 2;        // TMEM accumulator ring depth
+// How a launch divides K. The kernel is compiled once per (configuration, mode), so that the plain schedule — nearly
+// every launch — carries none of the three other epilogues: a quarter of the instructions, and registers to spare.
+enum KMode : int { kPlain = 0, kWorkspaceSplitK = 1, kClusterSplitK = 2, kStreamK = 3 };
+
+#ifndef B200_HGEMM_NO_K_DECOMP
+#define B200_HGEMM_NO_K_DECOMP 0     // experiment: kernels without split-K / stream-K code
+#endif
+#ifndef B200_HGEMM_SPLIT_SETUP
+#define B200_HGEMM_SPLIT_SETUP 0     // experiment: TMEM allocation after the barrier-publishing barrier, producer not waiting for it
+#endif
+#ifndef B200_HGEMM_EARLY_TMA
+#define B200_HGEMM_EARLY_TMA 0       // experiment: first loads before the set-up barrier (see the set-up block)
+#endif
 
 // Developer instrumentation (only in builds with -DB200_HGEMM_TRACE, i.e. libb200_hgemm_trace.so; the product build
 // contains none of it): per-CTA timestamps of the kernel's phases, read back by `dev_check_trace trace`.
@@ -73,7 +91,7 @@ __device__ __forceinline__ void trace_value(int slot, unsigned long long v) {
 #define B200_TRACE_ONLY(...)
 #endif
 
-template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1>
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1, int M_REP_ = 1>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
   static constexpr int STAGES = STAGES_;
@@ -87,11 +105,18 @@ struct Config {
   static constexpr int CLUSTER_N = CLUSTER_N_;
   static constexpr int MCAST_CTAS = CLUSTER_M * CLUSTER_N;
   static constexpr int CLUSTER_CTAS = CTA_GROUP * MCAST_CTAS;
-  static constexpr int TILE_M = kBlockM * CTA_GROUP;
+  // M_REP = 2: every CTA owns 256 rows — two 128-row MMAs per k-step that share the B tile in shared memory and fill
+  // two accumulators — so a CTA pair covers 512 x BN and each B byte fetched from L2 feeds twice the MMA work (the
+  // shape of cuBLAS's largest kernel, nvjet_hsh_256x256_64x4_2x1_2cta). With BN = 256 the two accumulators fill all
+  // 512 TMEM columns: no accumulator ring, the epilogue of a tile is not overlapped with the next main loop, which
+  // only a long K amortises. No split-K / stream-K in this mode.
+  static constexpr int M_REP = M_REP_;
+  static constexpr int CTA_M = kBlockM * M_REP;             // rows per CTA
+  static constexpr int TILE_M = CTA_M * CTA_GROUP;
   static constexpr int LOAD_N = BN / CTA_GROUP;             // B rows each CTA holds per stage
-  static constexpr int A_BOX_ROWS = kBlockM / CLUSTER_N;    // A rows each CTA loads per stage
+  static constexpr int A_BOX_ROWS = CTA_M / CLUSTER_N;      // A rows each CTA loads per stage
   static constexpr int B_BOX_ROWS = LOAD_N / CLUSTER_M;     // B rows each CTA loads per stage
-  static constexpr int A_STAGE_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int A_STAGE_BYTES = CTA_M * kBlockK * 2;
   static constexpr int B_STAGE_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_N = BN < 64 ? BN : 64;            // columns per epilogue step / TMA store box
@@ -99,21 +124,34 @@ struct Config {
   // two epilogue warps per TMEM lane quadrant share a tile's column chunks when there are at least two of them
   static constexpr int EPI_GROUPS = EPI_CHUNKS >= 2 ? 2 : 1;
   static constexpr int EPI_CHUNKS_PER_GROUP = (EPI_CHUNKS + EPI_GROUPS - 1) / EPI_GROUPS;
+  static constexpr int NUM_THREADS = EPI_GROUPS == 2 ? kNumThreads : kNumThreads - 128;   // no warps that would only wait
+  // which K-decompositions this configuration's kernel carries (B200_HGEMM_NO_K_DECOMP: an experiment build without
+  // any of them, to see what their code costs the plain path)
+  static constexpr bool SPLIT_K = !B200_HGEMM_NO_K_DECOMP && CTA_GROUP_ * CLUSTER_M_ * CLUSTER_N_ == 1 && BN_ >= 64 && M_REP_ == 1;
+  static constexpr bool STREAM_K = !B200_HGEMM_NO_K_DECOMP && CLUSTER_M_ * CLUSTER_N_ == 1 && BN_ >= 64 && M_REP_ == 1;
   static constexpr int EPI_BUF_BYTES = 32 * EPI_N * 2;       // one warp, one chunk: 32 rows x EPI_N fp16
   static constexpr int EPI_BYTES = 8 * 32 * 64 * 2;          // 8 warps x one staging buffer (sized for EPI_N = 64)
   static constexpr int BAR_BYTES = 512;
+  // stream-K, owner unit that ends a worker's schedule: the partial tiles are fetched by bulk copies into the (then
+  // idle) pipeline shared memory, one region per epilogue warp holding a ring of chunk images
+  static constexpr int FIX_REGION_BYTES = ((STAGES * STAGE_BYTES) / 8) & ~1023;
+  static constexpr int FIX_BARS = 8 * 3;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static constexpr int TMEM_COLS_USED = kAccStages * BN;
+  static constexpr int ACC_COLS = M_REP * BN;                // TMEM columns of one accumulator stage
+  static constexpr int ACC_STAGES = (kAccStages * ACC_COLS <= 512) ? kAccStages : 1;   // ring depth that fits TMEM
+  static constexpr int TMEM_COLS_USED = ACC_STAGES * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
                                  : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(BN == 32 || BN % 64 == 0, "tile N is 32 or a multiple of 64");
   static_assert(BN >= 32 && BN <= 256 && (BN % 16) == 0, "UMMA N constraints");
   static_assert(CLUSTER_CTAS <= 8, "portable cluster size");
   static_assert(A_BOX_ROWS % 8 == 0 && B_BOX_ROWS % 8 == 0, "slices must cover whole 8-row swizzle atoms");
+  static_assert(M_REP == 1 || M_REP == 2, "one or two 128-row blocks per CTA");
+  static_assert(A_BOX_ROWS <= 256 && B_BOX_ROWS <= 256, "TMA box dimension limit");
   static_assert(TMEM_COLS_USED <= 512, "accumulator ring exceeds TMEM");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KB alignment");
-  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert(8 * (2 * STAGES + 2 * kAccStages + 1) + 8 + 8 * FIX_BARS <= BAR_BYTES, "barrier block too small");   // ACC_STAGES <= kAccStages
 };
 
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
@@ -133,25 +171,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;   // SWIZZLE_128B
   return d;
 }
-
-struct TileCoord { int m_blk, n_blk; };
-
-// Grouped rasterisation: walk `group_m` row-blocks down before stepping one column-block right,
-// so a wave of CTAs shares a compact set of A/B panels in L2.
-__device__ __forceinline__ TileCoord tile_coord(int t, int num_m_blocks, int num_n_blocks, int group_m) {
-  const int tiles_per_group = group_m * num_n_blocks;
-  const int group = t / tiles_per_group;
-  const int first_m = group * group_m;
-  const int gsz = min(group_m, num_m_blocks - first_m);
-  const int in_group = t - group * tiles_per_group;
-  TileCoord c;
-  c.m_blk = first_m + in_group % gsz;
-  c.n_blk = in_group / gsz;
-  // serpentine: odd groups sweep N backwards, so the B panels touched last by one group are still in L2 for the next
-  if (group & 1) c.n_blk = num_n_blocks - 1 - c.n_blk;
-  return c;
-}
-
 
 constexpr int kMaxSplitTiles = 256;   // split-K is only used when tiles * splits <= #SMs
 
@@ -322,16 +341,299 @@ __device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int spli
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stream-K (hgemm_schedule.cuh). Partial tiles travel through the global workspace as REGISTER IMAGES: an epilogue
+// warp holds 32 rows x 64 accumulator columns of a chunk, one row per lane; the lanes write register quad i of the
+// chunk to 32 consecutive uint4 and the owner's same warp reads them back the same way, so both directions are
+// fully coalesced and no thread ever needs another thread's element. One flag per (CTA slot, epilogue warp):
+// raised by the contributor warp after its chunks are written, polled and lowered again by the owner warp, so the
+// warps stay as decoupled as in the plain epilogue and the flags are zero again when the grid ends.
+constexpr int kMaxStreamKSlots = 160;   // CTAs of a launch (>= 148 SMs), one partial-tile slot each
+constexpr int kStreamKFlagsPerSlot = 8; // epilogue warps
+constexpr bool kStreamKBulkFixup = true;   // false: always fetch the partials with register loads (streamk_own)
+
 template <class Cfg>
-__global__ void __launch_bounds__(kNumThreads, 1)
+struct StreamK {
+  static constexpr int REGS = Cfg::ACC_F32 ? Cfg::EPI_N : Cfg::EPI_N / 2;   // 32-bit registers per lane per chunk
+  static constexpr int R4 = REGS / 4;
+  static constexpr int CHUNK_U4 = R4 * 32;                                  // one warp, one chunk
+  static constexpr int SLOT_U4 = 4 * Cfg::EPI_CHUNKS * CHUNK_U4;            // one CTA: 128 rows x BN columns
+  static constexpr size_t SLOT_BYTES = size_t(SLOT_U4) * 16;
+  static constexpr uint32_t CHUNK_BYTES = uint32_t(CHUNK_U4) * 16;
+  static constexpr int FIX_RING = Cfg::FIX_REGION_BYTES / int(CHUNK_BYTES) >= 3 ? 3 : Cfg::FIX_REGION_BYTES / int(CHUNK_BYTES);
+};
+
+// this warp's chunk `j` of the accumulator, raw: fp32 bit patterns, or fp16 pairs (two columns per register)
+template <class Cfg>
+__device__ __forceinline__ void streamk_load_chunk(uint32_t taddr, uint32_t (&r)[StreamK<Cfg>::REGS]) {
+  using namespace ptx;
+  static_assert(Cfg::EPI_N == 64, "stream-K is wired for 64-column epilogue chunks");
+  if constexpr (Cfg::ACC_F32) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32b_x32(taddr, v0);
+    tmem_ld_32x32b_x32(taddr + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { r[i] = v0[i]; r[32 + i] = v1[i]; }
+  } else {
+    tmem_ld_32x32b_x32_pack16(taddr, r);
+    tmem_ld_wait();
+  }
+}
+
+// registers -> swizzled staging buffer -> TMA store of one 32 x EPI_N chunk (shared by the plain and the owner epilogue)
+template <class Cfg>
+__device__ __forceinline__ void epilogue_store_chunk(const uint32_t (&packed)[Cfg::EPI_N / 2], uint32_t epi_buf,
+                                                     uint32_t row_off, uint32_t sw, int lane,
+                                                     const CUtensorMap* tmap_c, int nc, int m0, int M, int N) {
+  using namespace ptx;
+  // the previous store from this warp's staging buffer must have finished reading it
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  const uint32_t dst = epi_buf + row_off;
+#pragma unroll
+  for (int c = 0; c < Cfg::EPI_N / 8; ++c)
+    st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
+      tma_store_2d(tmap_c, epi_buf, nc, m0);
+    tma_store_commit();
+  }
+}
+
+struct EpilogueWarp {          // what one epilogue warp knows about itself
+  int q, ew, lane;             // TMEM lane quadrant, index among the epilogue warps (0..7), lane
+  int j_begin, j_end;          // its share of a tile's column chunks
+  uint32_t epi_buf, row_off, sw;
+};
+
+// Contributor: spill this warp's chunks of the partial accumulator to the CTA's slot and raise the warp's flag.
+// `release_tmem` hands the accumulator stage back to the MMA warp as soon as the last chunk is in registers.
+template <class Cfg, class ReleaseTmem>
+__device__ __forceinline__ void streamk_contribute(const EpilogueWarp& w, uint32_t taddr0, uint4* __restrict__ ws,
+                                                   unsigned* __restrict__ flags, int slot, ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  uint4* base = ws + size_t(slot) * SK::SLOT_U4 + size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+#pragma unroll 1   // one chunk image (64 registers) at a time
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    uint32_t r[SK::REGS];
+    streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+    if (j == w.j_end - 1) release_tmem();
+    uint4* dst = base + size_t(j) * SK::CHUNK_U4;
+#pragma unroll
+    for (int i = 0; i < SK::R4; ++i) st_global_cg_v4(dst + i * 32, r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  }
+  __threadfence();   // every lane's stores are visible at gpu scope before lane 0 publishes the flag
+  __syncwarp();
+  if (w.lane == 0) st_release_gpu(flags + slot * kStreamKFlagsPerSlot + w.ew, 1u);
+}
+
+// Owner: the partials of `n` contributors (slots slot0, slot0 + slot_stride, ... — increasing k) summed in fp32 in that
+// fixed order, plus the own accumulator, rounded once, stored like any other tile. The partials were written long
+// before (they are their workers' first units), so the first chunk's are fetched BEFORE waiting for the own
+// accumulator (`wait_acc`): their L2 latency hides behind the tail of the main loop.
+template <class Cfg, class WaitAcc, class ReleaseTmem>
+__device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t taddr0, const uint4* __restrict__ ws,
+                                            unsigned* __restrict__ flags, int slot0, int slot_stride, int n,
+                                            const CUtensorMap* tmap_c, int m0, int n0, int M, int N,
+                                            WaitAcc wait_acc, ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  if (w.lane == 0) {
+    for (int p = 0; p < n; ++p) {
+      const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(f) == 0u) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { printf("b200_hgemm watchdog: stream-K slot %d never arrived\n", slot0 + p * slot_stride); __trap(); }
+      }
+    }
+  }
+  __syncwarp();
+  const size_t warp_off = size_t(w.q * Cfg::EPI_CHUNKS) * SK::CHUNK_U4 + w.lane;
+  // A chunk is summed in pieces of kPiece columns so that (sums + values in flight + own accumulator) stays near the
+  // register footprint of the plain epilogue: fp32 images in two pieces of 32 columns, fp16 images (half the
+  // registers) in one piece of 64.
+  constexpr int kPiece = Cfg::ACC_F32 ? 32 : 64;                  // columns
+  constexpr int kPieceQuads = SK::R4 * kPiece / Cfg::EPI_N;       // image quads per piece (8 in both cases)
+  constexpr int kBatch = 4;                                       // quads in flight per lane
+#pragma unroll 1
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    uint32_t packed[Cfg::EPI_N / 2];
+#pragma unroll
+    for (int h = 0; h < Cfg::EPI_N / kPiece; ++h) {
+      float f[kPiece];
+#pragma unroll
+      for (int i = 0; i < kPiece; ++i) f[i] = 0.f;
+      for (int p = 0; p < n; ++p) {
+        const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 + warp_off + size_t(j) * SK::CHUNK_U4 +
+                           size_t(h * kPieceQuads) * 32;
+#pragma unroll
+        for (int b = 0; b < kPieceQuads / kBatch; ++b) {
+          uint4 v[kBatch];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) v[i] = ld_global_cg_v4(src + (kBatch * b + i) * 32);
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const uint32_t x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if constexpr (Cfg::ACC_F32) {
+                f[4 * (kBatch * b + i) + c] += __uint_as_float(x[c]);
+              } else {
+                const __half2 hh = *reinterpret_cast<const __half2*>(&x[c]);
+                f[8 * (kBatch * b + i) + 2 * c] += __low2float(hh);
+                f[8 * (kBatch * b + i) + 2 * c + 1] += __high2float(hh);
+              }
+            }
+          }
+          __syncwarp();   // keeps the compiler from hoisting the next batch's loads above these sums
+        }
+      }
+      if (j == w.j_begin && h == 0) wait_acc();
+      const bool last = (j == w.j_end - 1) && (h == Cfg::EPI_N / kPiece - 1);
+      if constexpr (Cfg::ACC_F32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + j * Cfg::EPI_N + 32 * h, v);
+        tmem_ld_wait();
+        if (last) release_tmem();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          packed[16 * h + i] = pack_f16x2_rn(f[2 * i] + __uint_as_float(v[2 * i]), f[2 * i + 1] + __uint_as_float(v[2 * i + 1]));
+      } else {
+        uint32_t r[SK::REGS];
+        streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+        if (last) release_tmem();
+#pragma unroll
+        for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+          const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
+          packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+        }
+      }
+    }
+    epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
+  }
+  // lower the flags again: this warp is their only reader, and the next writer is a later launch
+  __syncwarp();
+  if (w.lane == 0)
+    for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
+}
+
+// Owner whose unit ends the worker's schedule: nothing hides the fix-up any more, and register loads would crawl
+// (one 16-byte load per lane and round trip). The pipeline shared memory is idle once the own accumulator is
+// complete, so lane 0 streams this warp's chunk images of every contributor through a ring of bulk copies
+// (`fix_smem`: this warp's region, `fix_bar`: its FIX_RING mbarriers, phase 0 on entry) while the warp sums them from
+// shared memory — same order of additions as streamk_own, hence the same bits.
+template <class Cfg, class WaitAcc, class ReleaseTmem>
+__device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t taddr0, const uint4* __restrict__ ws,
+                                                 unsigned* __restrict__ flags, int slot0, int slot_stride, int n,
+                                                 const CUtensorMap* tmap_c, int m0, int n0, int M, int N,
+                                                 uint32_t fix_smem, uint32_t fix_bar, WaitAcc wait_acc,
+                                                 ReleaseTmem release_tmem) {
+  using namespace ptx;
+  using SK = StreamK<Cfg>;
+  constexpr int RING = SK::FIX_RING;
+  static_assert(RING >= 2, "the fix-up ring needs two chunk images per epilogue warp");
+  if (w.lane == 0) {
+    for (int p = 0; p < n; ++p) {
+      const unsigned* f = flags + (slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(f) == 0u) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { printf("b200_hgemm watchdog: stream-K slot %d never arrived\n", slot0 + p * slot_stride); __trap(); }
+      }
+    }
+  }
+  __syncwarp();
+  const int total = (w.j_end - w.j_begin) * n;   // items in (chunk, contributor) order
+  auto issue = [&](int i) {
+    if (w.lane == 0) {
+      const int jj = i / n, p = i - jj * n, s = i % RING;
+      const uint4* src = ws + size_t(slot0 + p * slot_stride) * SK::SLOT_U4 +
+                         size_t(w.q * Cfg::EPI_CHUNKS + w.j_begin + jj) * SK::CHUNK_U4;
+      mbar_arrive_expect_tx(fix_bar + 8 * s, SK::CHUNK_BYTES);
+      bulk_load_1d(fix_smem + uint32_t(s) * SK::CHUNK_BYTES, src, SK::CHUNK_BYTES, fix_bar + 8 * s);
+    }
+  };
+  wait_acc();                 // every MMA of the worker has read its operands: the pipeline shared memory is free
+  fence_proxy_async_all();    // the partials were written through the generic proxy (by other CTAs, acquired above)
+  for (int i = 0; i < RING && i < total; ++i) issue(i);
+  int item = 0;
+#pragma unroll 1
+  for (int j = w.j_begin; j < w.j_end; ++j) {
+    float f[Cfg::EPI_N];
+#pragma unroll
+    for (int i = 0; i < Cfg::EPI_N; ++i) f[i] = 0.f;
+    for (int p = 0; p < n; ++p, ++item) {
+      const int s = item % RING;
+      mbar_wait(fix_bar + 8 * s, uint32_t(item / RING) & 1u);
+      const uint32_t img = fix_smem + uint32_t(s) * SK::CHUNK_BYTES + uint32_t(w.lane) * 16u;
+#pragma unroll
+      for (int i = 0; i < SK::R4; ++i) {
+        const uint4 v = ld_shared_v4(img + uint32_t(i) * 512u);
+        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if constexpr (Cfg::ACC_F32) {
+            f[4 * i + c] += __uint_as_float(x[c]);
+          } else {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&x[c]);
+            f[8 * i + 2 * c] += __low2float(hh);
+            f[8 * i + 2 * c + 1] += __high2float(hh);
+          }
+        }
+      }
+      __syncwarp();   // every lane is done with this ring slot
+      if (item + RING < total) {
+        fence_proxy_async_smem();
+        issue(item + RING);
+      }
+    }
+    uint32_t packed[Cfg::EPI_N / 2];
+    const bool last = (j == w.j_end - 1);
+    if constexpr (Cfg::ACC_F32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + j * Cfg::EPI_N + 32 * h, v);
+        tmem_ld_wait();
+        if (last && h == 1) release_tmem();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          packed[16 * h + i] = pack_f16x2_rn(f[32 * h + 2 * i] + __uint_as_float(v[2 * i]),
+                                             f[32 * h + 2 * i + 1] + __uint_as_float(v[2 * i + 1]));
+      }
+    } else {
+      uint32_t r[SK::REGS];
+      streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
+      if (last) release_tmem();
+#pragma unroll
+      for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
+        const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
+        packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+      }
+    }
+    epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
+  }
+  __syncwarp();
+  if (w.lane == 0)
+    for (int p = 0; p < n; ++p) flags[(slot0 + p * slot_stride) * kStreamKFlagsPerSlot + w.ew] = 0u;
+}
+
+template <class Cfg, int KMODE = kPlain>
+__global__ void __launch_bounds__(Cfg::NUM_THREADS, 1)
 hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {64, A_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_b,   // Bt [N,K]  box {64, B_BOX_ROWS}
                 const __grid_constant__ CUtensorMap tmap_c,   // C  [M,N]  box {EPI_N, 32}
                 int M, int N, int K, int group_m,
-                int splits,                       // split-K factor; > 1 only with CLUSTER_CTAS == 1, one unit per CTA
-                int cluster_reduce,               // 1: the `splits` CTAs of a unit form a cluster and reduce through DSMEM
-                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K)
-                unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] arrive / done counters, zero between launches
+                int splits_arg,                   // split-K factor (modes kWorkspaceSplitK / kClusterSplitK: one unit per CTA)
+                int sk_tiles_arg,                 // mode kStreamK: the first sk_tiles tiles are cut along K across all workers
+                float* __restrict__ splitk_ws,    // [units][128][BN] fp32 partial tiles (workspace split-K) / stream-K slots
+                unsigned* __restrict__ splitk_ctr,   // [2][kMaxSplitTiles] split-K arrive / done counters, then the
+                                                     // stream-K flags; all zero between launches
                 __half* __restrict__ c_raw,       // C base pointer, used by the split-K reductions' direct stores
                 uint64_t hint_a, uint64_t hint_b  /* L2 eviction priority of the A / B loads (ptx::kL2Evict*) */) {
   constexpr int BN = Cfg::BN;
@@ -340,6 +642,14 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   constexpr int CM = Cfg::CLUSTER_M;
   constexpr int CN = Cfg::CLUSTER_N;
   constexpr bool kMcast = Cfg::MCAST_CTAS > 1;
+  constexpr int AS = Cfg::ACC_STAGES;
+  constexpr int MR = Cfg::M_REP;
+  constexpr bool kSplit = (KMODE == kWorkspaceSplitK || KMODE == kClusterSplitK);
+  static_assert(!kSplit || Cfg::SPLIT_K, "this configuration has no split-K epilogues");
+  static_assert(KMODE != kStreamK || Cfg::STREAM_K, "this configuration has no stream-K epilogues");
+  // the schedule parameters a mode does not use are constants for it
+  const int splits = kSplit ? splits_arg : 1;
+  const int sk_tiles = (KMODE == kStreamK) ? sk_tiles_arg : 0;
   using namespace ptx;
 
   extern __shared__ uint8_t smem_raw[];
@@ -354,6 +664,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const uint32_t bar_tmem_empty = bar_tmem_full + 8 * kAccStages;
   const uint32_t bar_splitk = bar_tmem_empty + 8 * kAccStages;   // split-K: bulk loads of the partial slices
   const uint32_t tmem_slot = bar_splitk + 8;
+  const uint32_t bar_fix = tmem_slot + 8;                        // [8 epilogue warps][3]: stream-K fix-up rings
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x) >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -375,10 +686,9 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
   const int num_workers = gridDim.x / Cfg::CLUSTER_CTAS;   // clusters (or single CTAs)
   const int worker = blockIdx.x / Cfg::CLUSTER_CTAS;
-  // A work unit is (tile, k-split). splits == 1: units == tiles, walked persistently. splits > 1: the host
-  // launches exactly one CTA per unit, so the sibling splits of a tile run concurrently.
-  const int num_units = num_tiles * splits;
-  const int kb_per_split = (num_k_blocks + splits - 1) / splits;
+  // A work unit is (tile, k-block range), see hgemm_schedule.cuh. splits == 1: whole tiles walked persistently
+  // (after the worker's stream-K slice, if any). splits > 1: the host launches exactly one CTA per (tile, split)
+  // unit, so the sibling splits of a tile run concurrently.
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && elect_one()) {
@@ -386,16 +696,59 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx (the leader's, for a pair)
       mbar_init(bar_empty + 8 * s, kMcast ? CM + CN - 1 : 1);   // tcgen05.commit of every CTA this stage is shared with
     }
-    for (int a = 0; a < kAccStages; ++a) {
+    for (int a = 0; a < AS; ++a) {
       mbar_init(bar_tmem_full + 8 * a, 1);        // tcgen05.commit after the tile's last k-block
       mbar_init(bar_tmem_empty + 8 * a, 4 * Cfg::EPI_GROUPS * CG);  // one arrive per working epilogue warp of the group
     }
     mbar_init(bar_splitk, 1);
+    if constexpr (KMODE == kStreamK) {
+      for (int i = 0; i < Cfg::FIX_BARS; ++i) mbar_init(bar_fix + 8 * i, 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
+#if B200_HGEMM_EARLY_TMA
+    // Experiment (default off): a CTA that shares its barriers with nobody need not wait for the set-up barrier (and
+    // the TMEM allocation behind it) before its first loads leave — the first ring of the first unit is issued here,
+    // by the thread that has just initialised the barriers; the producer loop below starts behind it.
+    if constexpr (Cfg::CLUSTER_CTAS == 1) {
+      WorkIter first_work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+      WorkUnit u0;
+      if (first_work.next(u0)) {
+        fence_proxy_async_smem();   // the initialised barriers (generic proxy) before the loads' complete_tx (async proxy)
+        const TileCoord tc = tile_coord(u0.tile, num_m_blocks, num_n_blocks, group_m);
+        const int npre = min(STAGES, u0.kb1 - u0.kb0);
+        for (int st = 0; st < npre; ++st) {
+          mbar_arrive_expect_tx(bar_full + 8 * st, Cfg::STAGE_BYTES);
+          tma_load_2d_hint<1>(smem_a + st * Cfg::A_STAGE_BYTES, &tmap_a, bar_full + 8 * st, (u0.kb0 + st) * kBlockK,
+                              tc.m_blk * Cfg::TILE_M, hint_a);
+          tma_load_2d_hint<1>(smem_b + st * Cfg::B_STAGE_BYTES, &tmap_b, bar_full + 8 * st, (u0.kb0 + st) * kBlockK,
+                              tc.n_blk * BN, hint_b);
+        }
+      }
+    }
+#endif
   }
+#if B200_HGEMM_SPLIT_SETUP
+  // Experiment (default off): the barrier that publishes the initialised mbarriers comes first, the TMEM allocation
+  // after it, published by a second barrier that the producer warp does not take part in — its first loads are in
+  // flight while the allocator works.
+  __syncwarp();
+  if constexpr (Cfg::CLUSTER_CTAS > 1) cluster_sync_all(); else __syncthreads();
+  uint32_t tmem_base = 0;
+  if (warp != 0) {
+    if (warp == 2) {
+      tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish<CG>();
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    asm volatile("bar.sync 2, %0;" ::"n"(Cfg::NUM_THREADS - 32) : "memory");
+    tc_fence_after_sync();
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  }
+#else
   if (warp == 2) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish<CG>();
@@ -406,9 +759,10 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+#endif
   B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
-  int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
+  [[maybe_unused]] int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
 
   // ------------------------------------------------------------------ roles
   if (warp == 0) {
@@ -429,14 +783,26 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const uint32_t b_slice = uint32_t(cm) * (Cfg::B_BOX_ROWS * kBlockK * 2);
     int stage = 0; uint32_t phase = 0;
     B200_TRACE_ONLY(bool trace_first = true;)
-    for (int u = worker; u < num_units; u += num_workers) {
-      const int t = u / splits;
-      const int kb0 = (u - t * splits) * kb_per_split;
-      const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
-      const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM + cn * Cfg::A_BOX_ROWS;
+    WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+    WorkUnit u;
+#if B200_HGEMM_EARLY_TMA
+    bool skip_issued = (Cfg::CLUSTER_CTAS == 1);   // the first ring of the first unit left during set-up
+#endif
+    while (work.next(u)) {
+      const TileCoord tc = tile_coord(u.tile, num_m_blocks, num_n_blocks, group_m);
+      const int m0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M + cn * Cfg::A_BOX_ROWS;
       const int n0 = (tc.n_blk * CN + cn) * BN + int(cta_rank) * Cfg::LOAD_N + cm * Cfg::B_BOX_ROWS;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      int kb_begin = u.kb0;
+#if B200_HGEMM_EARLY_TMA
+      if (skip_issued) {
+        const int npre = min(STAGES, u.kb1 - u.kb0);
+        kb_begin += npre;
+        stage = npre % STAGES;
+        phase = uint32_t(npre / STAGES);
+        skip_issued = false;
+      }
+#endif
+      for (int kb = kb_begin; kb < u.kb1; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
           if (is_leader) mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES * CG);
@@ -457,7 +823,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc(Cfg::TILE_M, BN, Cfg::ACC_F32);
+      constexpr uint32_t idesc = make_idesc(kBlockM * CG, BN, Cfg::ACC_F32);   // one MMA covers 128 rows per CTA of the group
       const uint64_t desc_a0 = make_smem_desc(smem_a);
       const uint64_t desc_b0 = make_smem_desc(smem_b);
       // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
@@ -474,12 +840,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       B200_TRACE_ONLY(bool trace_first = true; unsigned long long trace_kb = 0, trace_units = 0;)
-      for (int u = worker; u < num_units; u += num_workers) {
-        const int kb0 = (u % splits) * kb_per_split;
-        const int kb1 = min(num_k_blocks, kb0 + kb_per_split);
+      WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+      WorkUnit u;
+      while (work.next(u)) {
+        const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(bar_tmem_empty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after_sync();
@@ -492,6 +859,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_f16<CG>(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            if constexpr (MR == 2) {
+              // the second 128-row block of this CTA's A tile (16 KB further into the stage) -> the second accumulator
+              constexpr uint64_t kSecondBlock = uint64_t((kBlockM * kBlockK * 2) >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_f16<CG>(tmem_d + BN, da + kSecondBlock + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((kb - kb0) | k) != 0);
+            }
             // free the smem slot everywhere it is shared once these MMAs have read it
             if constexpr (CG == 2 || kMcast) umma_commit_mcast<CG>(bar_empty + 8 * stage, mask_free);
             else umma_commit<CG>(bar_empty + 8 * stage);
@@ -503,7 +877,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        if (++acc == AS) { acc = 0; acc_phase ^= 1; }
         B200_TRACE_ONLY(++trace_units;)
       }
       B200_TRACE_ONLY(if (lane == 0) { B200_TRACE(5); B200_TRACE_VALUE(9, trace_kb); B200_TRACE_VALUE(11, trace_units); })
@@ -524,32 +898,70 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     const bool working = eg < Cfg::EPI_GROUPS;      // narrow tiles keep the second set of warps idle
     int acc = 0; uint32_t acc_phase = 0;
     B200_TRACE_ONLY(bool trace_first = true;)
+    const EpilogueWarp ew{q, warp - kEpiWarp0, lane, j_begin, j_end, epi_buf, row_off, sw};
     if (working) {
-    for (int u = worker; u < num_units; u += num_workers) {
-      const int t = u / splits;
+    WorkIter work(worker, num_workers, num_tiles, num_k_blocks, splits, sk_tiles);
+    WorkUnit u;
+    while (work.next(u)) {
+      const int t = u.tile;
       const TileCoord tc = tile_coord(t, num_m_blocks, num_n_blocks, group_m);
-      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * kBlockM;
-      const int m0 = m_tile0 + q * 32;
+      const int m_tile0 = (tc.m_blk * CM + cm) * Cfg::TILE_M + int(cta_rank) * Cfg::CTA_M;
       const int n0 = (tc.n_blk * CN + cn) * BN;
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
-        if (splits > 1 && eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
+      if constexpr (kSplit) {
+        if (eg != 0) break;   // the split-K reductions are written for the first four epilogue warps
       }
-      mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
-      tc_fence_after_sync();
-      B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) { if (trace_first) { B200_TRACE(6); trace_first = false; } B200_TRACE(10); })
-      const uint32_t taddr0 = tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16);
-      if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
-        if (splits > 1 && cluster_reduce) {
-          cluster_splitk_park<Cfg>(taddr0, q, lane, smem_a);
-          ck_m_base = m_tile0; ck_n0 = n0; ck_split = u - t * splits;
-          continue;   // the reduction runs after the cluster barrier below
+      const uint32_t taddr_acc = tmem_base + uint32_t(acc * Cfg::ACC_COLS) + (uint32_t(q * 32) << 16);
+      // the MMA warp's commit: this unit's accumulator is complete
+      auto wait_acc = [&] {
+        mbar_wait(bar_tmem_full + 8 * acc, acc_phase);
+        tc_fence_after_sync();
+        B200_TRACE_ONLY(if (warp == kEpiWarp0 && lane == 0) { if (trace_first) { B200_TRACE(6); trace_first = false; } B200_TRACE(10); })
+      };
+      // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
+      auto release_tmem = [&] {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
+          else mbar_arrive(tmem_empty0 + 8 * acc);
         }
-        if (splits > 1) {
-          splitk_epilogue<Cfg>(taddr0, q, lane, t, u - t * splits, splits, m_tile0, n0, M, N,
-                               splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
-          continue;   // one unit per CTA in split-K mode: no accumulator ring bookkeeping needed
+      };
+      [[maybe_unused]] uint4* ws4 = reinterpret_cast<uint4*>(splitk_ws);
+      [[maybe_unused]] unsigned* sk_flags = splitk_ctr + 2 * kMaxSplitTiles;
+      if constexpr (KMODE == kStreamK) {
+        if (u.kb0 == 0 && u.kb1 < num_k_blocks) {   // the head of a tile, which owns it
+          const int n = streamk_contributors(worker, num_workers, sk_tiles * num_k_blocks, t, num_k_blocks);
+          if (kStreamKBulkFixup && !work.has_more())   // nothing left to hide the fix-up behind: stream it through shared memory
+            streamk_own_bulk<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c,
+                                  m_tile0 + q * 32, n0, M, N, smem_a + uint32_t(ew.ew) * Cfg::FIX_REGION_BYTES,
+                                  bar_fix + 8 * 3 * ew.ew, wait_acc, release_tmem);
+          else
+            streamk_own<Cfg>(ew, taddr_acc, ws4, sk_flags, (worker + 1) * CG + int(cta_rank), CG, n, &tmap_c, m_tile0 + q * 32,
+                             n0, M, N, wait_acc, release_tmem);
+          if (++acc == AS) { acc = 0; acc_phase ^= 1; }
+          continue;
         }
       }
+      wait_acc();
+      // (split-K modes: one unit per CTA, so no accumulator ring bookkeeping is needed after it)
+      if constexpr (KMODE == kClusterSplitK) {
+        cluster_splitk_park<Cfg>(taddr_acc, q, lane, smem_a);
+        ck_m_base = m_tile0; ck_n0 = n0; ck_split = worker - t * splits;   // the reduction runs after the cluster barrier below
+      } else if constexpr (KMODE == kWorkspaceSplitK) {
+        splitk_epilogue<Cfg>(taddr_acc, q, lane, t, worker - t * splits, splits, m_tile0, n0, M, N,
+                             splitk_ws, splitk_ctr, c_raw, smem_a, bar_splitk);
+      } else {
+      if constexpr (KMODE == kStreamK) {
+        if (u.kb0 > 0) {   // a later part of a tile's k-range, handed to the tile's owner
+          streamk_contribute<Cfg>(ew, taddr_acc, ws4, sk_flags, worker * CG + int(cta_rank), release_tmem);
+          if (++acc == AS) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < MR; ++r) {   // the 128-row blocks of this CTA's tile, one accumulator each
+      const uint32_t taddr0 = taddr_acc + uint32_t(r * BN);
+      const int m0 = m_tile0 + r * kBlockM + q * 32;
       for (int j = j_begin; j < j_end; ++j) {
         uint32_t packed[EN / 2];
         if constexpr (Cfg::ACC_F32) {
@@ -573,33 +985,12 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);
           tmem_ld_wait();
         }
-        if (j == j_end - 1) {
-          // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty0 + 8 * acc);
-            else mbar_arrive(tmem_empty0 + 8 * acc);
-          }
-        }
-        // the previous store from this warp's staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        const uint32_t dst = epi_buf + row_off;
-#pragma unroll
-        for (int c = 0; c < EN / 8; ++c)
-          st_shared_v4(dst + ((uint32_t(c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1],
-                       packed[4 * c + 2], packed[4 * c + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const int nc = n0 + j * EN;
-          if (m0 < M && nc < N)   // rows/cols past the edge are clipped by the tensor map
-            tma_store_2d(&tmap_c, epi_buf, nc, m0);
-          tma_store_commit();
-        }
+        if (j == j_end - 1 && r == MR - 1) release_tmem();
+        epilogue_store_chunk<Cfg>(packed, epi_buf, row_off, sw, lane, &tmap_c, n0 + j * EN, m0, M, N);
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      if (++acc == AS) { acc = 0; acc_phase ^= 1; }
+      }   // plain / stream-K modes
     }
     }
     // smem may be released once the bulk stores have READ it; their global writes complete with the grid
@@ -608,15 +999,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
   }
 
   // ------------------------------------------------------------------ cluster split-K reduction
-  if constexpr (Cfg::CLUSTER_CTAS == 1 && BN >= 64) {
-    if (splits > 1 && cluster_reduce) {
-      __syncwarp();
-      cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
-      if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4)
-        cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
-      __syncwarp();
-      cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
-    }
+  if constexpr (KMODE == kClusterSplitK) {
+    __syncwarp();
+    cluster_sync_all();   // every split's partial tile is parked in its CTA's shared memory
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4)
+      cluster_splitk_reduce<Cfg>((warp - kEpiWarp0) * 32 + lane, ck_split, splits, ck_m_base, ck_n0, M, N, smem_a, c_raw);
+    __syncwarp();
+    cluster_sync_all();   // no CTA leaves (and frees its smem) while a peer may still be reading it
   }
 
   // ------------------------------------------------------------------ teardown

@@ -47,6 +47,9 @@ int b200_hgemm_config_info(int config_id, int* bn, int* stages, int* cta_group);
 /* TMA-multicast cluster shape of a configuration (1 x 1 = none): cluster_m x cluster_n single-CTA groups work on
  * adjacent tiles; A tiles are shared along N, B tiles along M. */
 int b200_hgemm_config_cluster(int config_id, int* cluster_m, int* cluster_n);
+/* 128-row blocks per CTA: 1, or 2 for the configurations whose CTAs own 256 rows (two MMAs per k-step that share the
+ * B tile in shared memory); the tile is then 128 * m_rep * cta_group rows. Negative status for an unknown id. */
+int b200_hgemm_config_m_rep(int config_id);
 /* The configuration the dispatcher uses for this problem (acc_bits = 32 or 16). */
 int b200_hgemm_select_config(int acc_bits, int M, int N, int K);
 /* Same, also reporting the rasterisation group (0 = kernel default) and the split-K factor (1 = none).
@@ -55,9 +58,20 @@ int b200_hgemm_select(int acc_bits, int M, int N, int K, int* config_id, int* gr
 /* Run one explicit configuration. group_m <= 0 and max_ctas <= 0 select the defaults; splits > 1 asks for
  * split-K through a lazily allocated per-stream fp32 workspace (cta_group 1 configurations only; clamped so
  * that tiles x splits fits the SMs); splits = -2, -4 or -8 asks for split-K inside a thread-block cluster of that
- * many CTAs, reduced through distributed shared memory (no workspace). Both reductions are deterministic. */
+ * many CTAs, reduced through distributed shared memory (no workspace); splits = 100 asks for stream-K over the tiles of
+ * the partial last wave, 101 for stream-K over that tail plus one full wave (both through the workspace; cta_group 1
+ * and 2, no multicast cluster; ignored when the tile count already fills the last wave). All reductions are
+ * deterministic. */
 int b200_hgemm_run_config(int acc_bits, int config_id, const void* A, const void* B_kmajor, void* C,
                           int M, int N, int K, int group_m, int max_ctas, int splits, void* stream);
+
+/* Host-only view of the kernel's schedule (no device needed): the work units worker `worker` runs, in order, on a
+ * device with num_sms SMs, as triples (tile, first k-block, end k-block) written to units[3 * max_units]. Also
+ * reports the number of workers (CTAs, CTA pairs or clusters) of the launch, the stream-K tile count, and per unit
+ * the number of contributor units an owner unit waits for (NULL to skip). Returns the worker's unit count
+ * (possibly > max_units) or a negative status. The same code walks the schedule inside the kernel. */
+int b200_hgemm_schedule_units(int config_id, int M, int N, int K, int splits, int num_sms, int worker, int* units,
+                              int max_units, int* num_workers, int* sk_tiles, int* contributors);
 
 /* End-to-end form with HOST buffers (pageable or pinned): copies A and B_kmajor to the device,
  * runs the GEMM and copies C back, synchronising before it returns. This is the call bench.py

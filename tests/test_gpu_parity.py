@@ -111,6 +111,46 @@ def test_split_k_is_exact_deterministic_and_self_resetting(acc):
 
 
 @pytest.mark.parametrize("acc", ACCS)
+def test_stream_k_is_exact_deterministic_and_self_resetting(acc):
+    """Stream-K (tile counts that do not fill the last wave): bit-exact on 0/1 operands for single CTAs and CTA pairs,
+    one and many contributors per tile, ragged edges; identical bits run to run on N(0,1) operands; repeated launches
+    work (every flag is lowered by its reader); and the stream-K schedule really was in effect."""
+    cfgs = capi.configs()
+    plain = [c for c in cfgs if c["cluster_m"] * c["cluster_n"] == 1 and c["bn"] >= 64]
+    # (shape, max_ctas): few tiles on all SMs (many contributors per tile), several waves + a tail on a few CTAs
+    # (one or two contributors, stream-K followed by data-parallel tiles), ragged edges
+    cases = [((512, 768, 4096), 0), ((1024, 1536, 1024), 20), ((1000, 1224, 2048), 28), ((384, 4096, 8192), 0),
+             ((2048, 2048, 512), 36)]
+    for (m, n, k), max_ctas in cases:
+        a, bt = oracle.fill_zero_one((m, k), 3, 21), oracle.fill_zero_one((n, k), 3, 22)
+        want = oracle.hgemm_f32acc(a, bt, fast=True)
+        da, dbt = dev(a), dev(bt)
+        for c in plain:
+            if c["cta_group"] == 2 and m <= 128:
+                continue
+            for mode in (capi.STREAMK_TAIL, capi.STREAMK_TAIL_PLUS_WAVE):
+                sched = capi.schedule(c["id"], m, n, k, mode, max_ctas or 148)
+                for _ in range(2):
+                    got = run(da, dbt, acc, cfg=c["id"], splits=mode, max_ctas=max_ctas).cpu().numpy()
+                    assert np.array_equal(got, want), (acc, c, mode, m, n, k, max_ctas, sched["sk_tiles"])
+    # the cases above are not vacuous: most (config, case) pairs do run a stream-K schedule
+    active = sum(capi.schedule(c["id"], m, n, k, capi.STREAMK_TAIL, mc or 148)["sk_tiles"] > 0
+                 for c in plain for (m, n, k), mc in cases)
+    assert active >= len(plain) * len(cases) // 2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn((512, 8192), device="cuda", generator=g).half()
+    bt = torch.randn((2048, 8192), device="cuda", generator=g).half()
+    for cfg in (0, 3):
+        first = run(a, bt, acc, cfg=cfg, splits=capi.STREAMK_TAIL)
+        plain_c = run(a, bt, acc, cfg=cfg)
+        for _ in range(3):
+            assert torch.equal(run(a, bt, acc, cfg=cfg, splits=capi.STREAMK_TAIL), first)
+        # a different summation grouping, not a different result: within a few fp16 ulps of the unsplit kernel
+        err = (first.float() - plain_c.float()).abs()
+        assert float(err.max()) <= (0.25 if acc == "fp32" else 2.0), float(err.max())
+
+
+@pytest.mark.parametrize("acc", ACCS)
 def test_randn_golden_within_stated_tolerance(randn_cases, acc):
     for c in randn_cases:
         got = run(dev(c["a"]), dev(c["b"].T), acc).cpu().numpy().astype(np.float32)
@@ -177,12 +217,20 @@ def test_size_independent_properties_at_full_size(acc):
 
 
 def test_host_buffer_entry_point_round_trips():
-    m, n, k = 512, 768, 256
-    a = torch.from_numpy(oracle.fill_zero_one((m, k), 2, 5)).pin_memory()
-    bt = torch.from_numpy(oracle.fill_zero_one((n, k), 2, 6)).pin_memory()
-    c = torch.empty((m, n), dtype=torch.half).pin_memory()
-    capi.hgemm_host(a, bt.reshape(k, n), c, "fp32")
-    assert np.array_equal(c.numpy(), oracle.hgemm_f32acc(a.numpy(), bt.numpy(), fast=True))
+    # small: one copy in, one GEMM, one copy out; large: B first, then A / GEMM / C in four pipelined row blocks
+    # (ragged M: the last block is shorter), from pinned and from pageable memory, twice (streams and events are reused)
+    for (m, n, k), acc in (((512, 768, 256), "fp32"), ((4096, 2048, 1024), "fp32"), ((3000, 1224, 2048), "fp16")):
+        a_np, bt_np = oracle.fill_zero_one((m, k), 3, 5), oracle.fill_zero_one((n, k), 3, 6)
+        want = oracle.hgemm_f32acc(a_np, bt_np, fast=True)
+        for pinned in (True, False):
+            a, bt = torch.from_numpy(a_np.copy()), torch.from_numpy(bt_np.copy())
+            c = torch.full((m, n), float("nan"), dtype=torch.half)
+            if pinned:
+                a, bt, c = a.pin_memory(), bt.pin_memory(), c.pin_memory()
+            for _ in range(2):
+                c.fill_(float("nan"))
+                capi.hgemm_host(a, bt.reshape(k, n), c, acc)
+                assert np.array_equal(c.numpy(), want), (m, n, k, acc, pinned)
 
 
 def test_errors_are_loud():
