@@ -55,6 +55,14 @@ for acc in 32 16; do run check $acc 26 4096 4096 4096 8; run check $acc 26 1000 
 for shape in "8192 8192 8192" "16384 16384 16384" "16384 16384 4096" "4096 12288 16384" "4096 4096 4096" "8192 8192 2048"; do
   for cfg in 3 26 27 28; do run time 32 $cfg $shape 10 8 1; done
 done
+echo "== 3c. sustain (2 s): burst vs power-capped, headline shapes, candidate configs" >> $LOG
+for spec in "6 4096 4096 4096 8 1" "6 4096 4096 4096 8 100" "3 4096 4096 4096 8 1" "3 4096 4096 4096 8 100" "20 4096 4096 4096 8 1" "21 4096 4096 4096 8 1" "29 4096 4096 4096 8 1" "26 4096 4096 4096 8 1" \
+            "3 8192 8192 8192 8 1" "26 8192 8192 8192 8 1" "27 8192 8192 8192 8 1" "29 8192 8192 8192 8 1" "3 2048 11008 4096 8 1" "6 2048 11008 4096 8 1"; do
+  set -- $spec
+  run sustain 32 $1 $2 $3 $4 2.0 $5 $6
+done
+echo "== 3d. bench.py (pipelined e2e)" >> $LOG
+timeout 600 python bench.py --steps 200 --warmup 10 --cpu_seconds 2 >> $LOG 2>&1
 echo "== 4. pytest" >> $LOG
 timeout 1200 python -m pytest tests -m gpu -x -q >> $LOG 2>&1; echo "pytest rc=$?" >> $LOG
-grep -E "FAIL|exit|watchdog|TIME|pytest rc|passed|failed" $LOG | tail -60
+grep -E "FAIL|exit|watchdog|TIME|SUSTAIN|pytest rc|passed|failed|\"metric\"" $LOG | cut -c1-400 | tail -120
