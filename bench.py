@@ -22,6 +22,13 @@ What is timed
   --impl reference   times that same CPU path as the whole job (the reference has no other CPU implementation
           and its GPU kernels target sm_80/sm_90 — see DESIGN.md), K bounded steps, rank 0 only.
 
+  sustained  the same step loop run for ~1 s (the power-capped state a long job lives in), reported beside the burst value.
+  sweep   BASELINE config 5: the 1000-shape grid (+ 2048_11008_4096) through the same C ABI, shapes dealt to the ranks
+          (one problem per GPU at a time, no collective on the GEMM path). Per shape: the harness metric (host clock
+          around one call bracketed by device synchronisation, mean of per-sample TFLOP/s, benchmarking_utils.py:23-31)
+          and a CUDA-event-timed back-to-back batch. Aggregate = sum of 2MNK over ALL shapes / max over ranks of the
+          rank's summed device time, so it grows with N only if the sharding works.
+
 Multi-GPU: the path shards by problem (one GEMM per GPU, no collective on the data path), so
 at N > 1 every rank runs the same per-GPU work ("scaling": "weak") and value is the sum over ranks.
 """
@@ -57,6 +64,10 @@ def parse_args():
     p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     p.add_argument("--e2e_steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 50))")
     p.add_argument("--cpu_seconds", type=float, default=10.0, help="bound on the cpu_baseline sample")
+    p.add_argument("--sustained_seconds", type=float, default=1.0, help="length of the power-capped loop (0 = skip)")
+    p.add_argument("--sweep", type=str, default="grid", help="'grid' (1001 shapes), 'none', or a comma list of M_N_K")
+    p.add_argument("--sweep_ms", type=float, default=12.0, help="sampling budget per shape of the sweep leg")
+    p.add_argument("--cpu_threads", type=int, default=0, help="threads of the CPU arms (0 = half the host's logical CPUs)")
     return p.parse_args()
 
 
@@ -159,13 +170,23 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "source": source}
 
 
+def set_cpu_threads(requested: int) -> int:
+    """Thread count of the CPU arms, set explicitly: torchrun exports OMP_NUM_THREADS=1, which would turn the reference
+    arm at N > 1 into a one-thread run (and inflate every ratio computed from it). Default: half the logical CPUs
+    (= the physical cores of an SMT-2 host), the count torch itself picks when nothing overrides it."""
+    n = requested if requested > 0 else max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def reference_cpu_step(a32, b32):
     return torch.matmul(a32, b32).half()          # the reference's truth path (zero_one_correctness_check.py:87-90)
 
 
-def cpu_baseline(m, n, k, seconds: float) -> dict:
+def cpu_baseline(m, n, k, seconds: float, threads: int) -> dict:
     import oracle  # the one place bench.py may use oracle/: the reported CPU baseline (never the measured path)
 
+    cores = set_cpu_threads(threads)
     g = torch.Generator().manual_seed(0)
     a = torch.randn((m, k), generator=g).half()
     b = torch.randn((k, n), generator=g).half()
@@ -178,9 +199,9 @@ def cpu_baseline(m, n, k, seconds: float) -> dict:
         if (reps >= 3 and el >= seconds) or el >= 3 * seconds:
             break
     tf = 2.0 * m * n * k * reps / el * 1e-12
-    return {"value": tf, "unit": "TFLOP/s", "cores": oracle.cpu_threads(), "host_cpus": os.cpu_count(),
+    return {"value": tf, "unit": "TFLOP/s", "cores": cores, "host_cpus": os.cpu_count(),
             "kind": "reference",
-            "sample": f"{reps} x torch.matmul(a.cpu().float(), b.cpu().float()).half() at {m}x{n}x{k} in {el:.1f} s"}
+            "sample": f"{reps} x torch.matmul(a.cpu().float(), b.cpu().float()).half() at {m}x{n}x{k} in {el:.1f} s on {cores} threads"}
 
 
 def run_reference(args, m, n, k, rank, world):
@@ -189,6 +210,7 @@ def run_reference(args, m, n, k, rank, world):
         return
     import oracle
 
+    cores = set_cpu_threads(args.cpu_threads)
     g = torch.Generator().manual_seed(0)
     a = torch.randn((m, k), generator=g).half()
     b = torch.randn((k, n), generator=g).half()
@@ -206,7 +228,6 @@ def run_reference(args, m, n, k, rank, world):
             break
     el = time.perf_counter() - t0
     tf = per_step * done / el * 1e-12
-    cores = oracle.cpu_threads()
     sample = f"{done} of {steps} requested steps, each one {m}x{n}x{k} fp32 torch.matmul + .half() on {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": "HGEMM TFLOP/s, offline mode, per (M,N,K)", "value": tf, "unit": "TFLOP/s",
@@ -216,10 +237,111 @@ def run_reference(args, m, n, k, rank, world):
         "config": {"workload": f"{m}_{n}_{k} --acc_precise {args.acc} --mode offline", "parallelism": "cpu threads",
                    "note": "reference CPU path = its ground-truth expression; its GPU kernels target sm_80/sm_90"},
         "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "host_cpus": os.cpu_count(),
-                         "kind": "reference", "sample": sample},
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "kind": "reference", "sample": sample},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def sweep_shapes(spec: str):
+    from cuda_l2_b200 import farm
+
+    if spec == "grid":
+        return farm.grid_shapes()
+    return [tuple(int(x) for x in s.split("_")) for s in spec.split(",") if s]
+
+
+def sweep_cost(shape) -> float:
+    """Seconds one shape costs a rank in the sweep leg (sampling budget floor + a handful of calls)."""
+    m, n, k = shape
+    t = max(2.0 * m * n * k / 1.3e15, 2.0 * (m * k + n * k + m * n) / 5.5e12, 6e-6)
+    return 0.014 + 9 * t
+
+
+def sweep_partition(shapes, world: int):
+    """Longest-first onto the least loaded rank (the farm's rule with this leg's cost model)."""
+    loads = [0.0] * world
+    parts = [[] for _ in range(world)]
+    for s in sorted(shapes, key=lambda s: (-sweep_cost(s), s)):
+        r = min(range(world), key=lambda i: (loads[i], i))
+        parts[r].append(s)
+        loads[r] += sweep_cost(s)
+    return parts
+
+
+def run_sweep(args, capi, rank: int, world: int, dist) -> dict | None:
+    """BASELINE config 5 on this job's GPUs. Returns the report on rank 0."""
+    shapes = sweep_shapes(args.sweep)
+    mine = sweep_partition(shapes, world)[rank]
+    lib = capi.hgemm_lib()
+    fn = lib.b200_hgemm_f32acc if args.acc == "fp32" else lib.b200_hgemm_f16acc
+    max_e = max(max(m * k, n * k, m * n) for m, n, k in shapes)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    buf_a = torch.randn(max_e, device="cuda", generator=g).half()
+    buf_b = torch.randn(max_e, device="cuda", generator=g).half()
+    buf_c = torch.empty(max_e, dtype=torch.half, device="cuda")
+    pa, pb, pc = buf_a.data_ptr(), buf_b.data_ptr(), buf_c.data_ptr()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync, clock = torch.cuda.synchronize, time.perf_counter
+    budget = args.sweep_ms * 1e-3
+    launches0 = capi.launch_count()
+    recs = []
+    sync()
+    t_leg0 = clock()
+    for (m, n, k) in mine:
+        def call():
+            st = fn(pa, None, pb, pc, m, n, k, None)
+            if st:
+                raise RuntimeError(f"b200_hgemm failed on {m}x{n}x{k}: {capi.strerror(st)}")
+        flops = 2.0 * m * n * k
+        call(); call(); sync()
+        # the harness metric: host clock around ONE call bracketed by device synchronisation
+        tf_sum, ms_sum, cnt, t_shape = 0.0, 0.0, 0, clock()
+        while cnt < 3 or (clock() - t_shape < budget and cnt < 200):
+            sync(); t0 = clock(); call(); sync(); dt = clock() - t0
+            tf_sum += flops / dt * 1e-12; ms_sum += dt * 1e3; cnt += 1
+        # device time of back-to-back calls (offline throughput), CUDA events on the launching stream
+        reps = max(3, min(64, int(2e-3 / max(ms_sum / cnt * 1e-3, 1e-6))))
+        e0.record()
+        for _ in range(reps):
+            call()
+        e1.record(); sync()
+        recs.append((m, n, k, tf_sum / cnt, ms_sum / cnt, e0.elapsed_time(e1) / reps))
+    sync()
+    leg_s = clock() - t_leg0
+    launches = capi.launch_count() - launches0
+    dev_s = sum(r[5] for r in recs) * 1e-3
+    mine_report = {"rank": rank, "shapes": len(recs), "device_s": dev_s, "leg_s": leg_s, "launches": launches,
+                   "flops": sum(2.0 * r[0] * r[1] * r[2] for r in recs), "recs": recs}
+    if dist is not None:
+        bucket = [None] * world if rank == 0 else None
+        dist.gather_object(mine_report, bucket, dst=0)
+    else:
+        bucket = [mine_report]
+    if rank != 0:
+        return None
+    peak_tf, peak_hbm, _, _ = peaks()
+    allrecs = [r for b in bucket for r in b["recs"]]
+    total_flops = sum(b["flops"] for b in bucket)
+    makespan_dev = max(b["device_s"] for b in bucket)
+    roof_s = sum(max(2.0 * m * n * k / (peak_tf * 1e12), 2.0 * (m * k + n * k + m * n) / (peak_hbm * 1e9))
+                 for m, n, k, *_ in allrecs)
+    named = {f"{m}_{n}_{k}": {"harness_tflops": tf, "device_us": us * 1e3}
+             for m, n, k, tf, _, us in allrecs if (m, n, k) in ((64, 4096, 64), (4096, 4096, 4096), (8192, 8192, 8192), (2048, 11008, 4096))}
+    return {
+        "what": "BASELINE config 5: every (M,N,K) of the grid once per job, shapes dealt longest-first to the ranks, no collective on the GEMM path",
+        "shapes": len(allrecs), "acc": args.acc,
+        "aggregate_tflops": total_flops / makespan_dev * 1e-12,       # whole sweep / slowest rank's summed device time
+        "aggregate_definition": "sum(2MNK over all shapes) / max over ranks of sum(per-shape CUDA-event time of back-to-back calls)",
+        "sum_device_s": sum(b["device_s"] for b in bucket), "makespan_device_s": makespan_dev,
+        "makespan_wall_s": max(b["leg_s"] for b in bucket),
+        "harness_mean_tflops": sum(r[3] for r in allrecs) / len(allrecs),   # the reference's per-shape metric, averaged
+        "roofline_frac": roof_s / sum(b["device_s"] for b in bucket),       # sum of per-shape roofline minima / measured
+        "roofline_min_s": roof_s,
+        "per_rank": [{k: b[k] for k in ("rank", "shapes", "device_s", "leg_s", "launches")} for b in bucket],
+        "baseline_config_shapes": named,
+        "l2_policy": "operands of a shape stay where the previous call left them (L2-resident when they fit), as in the reference harness which times a call right after writing its operands",
+    }
 
 
 def main():
@@ -263,6 +385,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     warm = max(args.warmup, 3)
     for i in range(warm):
         step(i)
@@ -281,16 +410,27 @@ def main():
     e1.record()
     barrier()
     launches = capi.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     if dist is not None:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
     flops_step = 2.0 * m * n * k
     value = flops_step * args.steps * world / (ms_total * 1e-3) * 1e-12
+
+    # ---- sustained: the same loop for about a second (power-capped clocks), same timing rules
+    sustained = None
+    if args.sustained_seconds > 0:
+        sus_steps = max(args.steps, int(args.sustained_seconds / max(ms_total / args.steps * 1e-3, 1e-6)))
+        barrier()
+        e0.record()
+        for i in range(sus_steps):
+            step(i)
+        e1.record()
+        barrier()
+        sus_ms = max_over_ranks(e0.elapsed_time(e1))
+        sustained = {"value": flops_step * sus_steps * world / (sus_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "steps": sus_steps,
+                     "ms_per_step": sus_ms / sus_steps, "seconds": sus_ms * 1e-3}
 
     # ---- end-to-end leg: host buffers through the C ABI, copies inside the timed region
     ha = torch.randn((m, k)).half().pin_memory()
@@ -304,23 +444,43 @@ def main():
     for _ in range(e2e_steps):
         capi.hgemm_host(ha, hbt.view(k, n), hc, args.acc)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = flops_step * e2e_steps * world / e2e_s * 1e-12
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- BASELINE config 5: the shape sweep sharded over this job's GPUs
+    sweep = None
+    if args.sweep != "none":
+        del sets
+        torch.cuda.empty_cache()
+        barrier()
+        sweep = run_sweep(args, capi, rank, world, dist)
+        if dist is not None:
+            lt = torch.tensor([capi.launch_count() - launches0], device="cuda", dtype=torch.int64)
+            dist.all_reduce(lt)
+            total_launches = int(lt.item())
+        else:
+            total_launches = capi.launch_count() - launches0
+    else:
+        total_launches = None
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src, peak_sustained = peaks()
-        achieved = flops_step / (ms_total / args.steps * 1e-3) * 1e-12      # per launch, from the CUDA events above
+        sec_per_launch = ms_total / args.steps * 1e-3                      # per launch, from the CUDA events above
+        ai = (m * n * k) / (m * k + n * k + m * n)                         # FLOP per byte
+        ridge = peak_tf * 1e12 / (peak_hbm * 1e9)
+        if ai >= ridge:
+            bound, achieved, peak, unit = "tensor", flops_step / sec_per_launch * 1e-12, peak_tf, "TFLOP/s"
+        else:
+            bound, achieved, peak, unit = "hbm", set_bytes / sec_per_launch * 1e-9, peak_hbm, "GB/s"
         cfg_id, group_m, splits = capi.select(args.acc, m, n, k)
         cfg = capi.configs()[cfg_id]
-        traffic = None
+        traffic, traffic_src = None, None
         tf = REPO / "profiles" / "dram_traffic.json"
         if tf.exists():
             traffic = json.loads(tf.read_text()).get(f"{args.mnk}_{args.acc}")
+            traffic_src = ("profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
+                           "capture of this kernel on this workload (a profiler run, NOT measured inside this timed run)")
         out = {
             "metric": "HGEMM TFLOP/s, offline mode, per (M,N,K)",
             "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -332,17 +492,23 @@ def main():
                        "kernel_config": {"tile": f"{128 * cfg['cta_group'] * cfg.get('m_rep', 1)}x{cfg['bn']}x64", "stages": cfg["stages"],
                                          "cta_group": cfg["cta_group"], "cluster": f"{cfg['cluster_m']}x{cfg['cluster_n']}", "group_m": group_m,
                                          "split_k": splits}},
+            "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * (m * k + n * k),
                     "d2h_bytes_per_step": 2 * m * n, "steps": e2e_steps, "api": "b200_hgemm_host (pinned host buffers)"},
             "gpu_launches": launches,
+            "gpu_launches_all_legs": total_launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                         "peak_sustained": peak_sustained, "frac_of_sustained": (achieved / peak_sustained) if peak_sustained else None,
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "arithmetic_intensity": ai, "ridge": ridge,
+                         "peak_sustained": peak_sustained if bound == "tensor" else None,
+                         "frac_sustained_of_sustained_peak": (sustained["value"] / world / peak_sustained)
+                         if (sustained and peak_sustained and bound == "tensor") else None,
                          "algorithmic_flops_per_launch": flops_step, "algorithmic_bytes_per_launch": set_bytes},
+            "sweep": sweep,
         }
         if world == 1:
-            out["cpu_baseline"] = cpu_baseline(m, n, k, args.cpu_seconds)
+            out["cpu_baseline"] = cpu_baseline(m, n, k, args.cpu_seconds, args.cpu_threads)
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()

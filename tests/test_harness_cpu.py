@@ -1,5 +1,6 @@
 """Host-side harness logic that needs no GPU: build glue, padding rule, 0/1 check plumbing, summary, CLI."""
 import json
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -161,6 +162,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"].startswith("256_512_128") and d["steps"] == 2
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_ignores_torchruns_one_thread_default():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use the host's cores (round-1 SCALE ratios at
+    N > 1 were inflated ~7.6x by a one-thread reference) and say how many it used."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--mnk", "256_512_128", "--steps", "1",
+                        "--warmup", "1", "--gpus", "2"], cwd=REPO, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    want = max(1, (os.cpu_count() or 2) // 2)
+    assert d["cpu_baseline"]["cores"] == want and d["cpu_baseline"]["omp_num_threads_env"] == "1" and d["n_gpus"] == 2
+    # a non-zero rank of the reference arm prints nothing and exits 0
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--mnk", "256_512_128", "--steps", "1",
+                        "--gpus", "2"], cwd=REPO, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_bench_sweep_partition_covers_every_shape_once_and_balances():
+    import bench
+    shapes = bench.sweep_shapes("grid")
+    assert len(shapes) == 1001 and (2048, 11008, 4096) in shapes
+    for world in (1, 2, 4, 8):
+        parts = bench.sweep_partition(shapes, world)
+        flat = [s for part in parts for s in part]
+        assert sorted(flat) == sorted(shapes) and len(set(flat)) == 1001
+        loads = [sum(bench.sweep_cost(s) for s in part) for part in parts]
+        assert max(loads) <= 1.02 * (sum(loads) / world) + bench.sweep_cost((16384, 16384, 16384))
+    assert bench.sweep_shapes("64_4096_64,4096_4096_4096") == [(64, 4096, 64), (4096, 4096, 4096)]
 
 
 def test_bench_without_a_gpu_fails_loudly():
