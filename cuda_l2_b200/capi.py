@@ -50,6 +50,8 @@ def hgemm_lib() -> ctypes.CDLL:
         ip = ctypes.POINTER(i)
         lib.b200_hgemm_schedule_units.argtypes = [i, i, i, i, i, i, i, ip, i, ip, ip, ip]
         lib.b200_hgemm_schedule_units.restype = i
+        lib.b200_hgemm_prewarm.argtypes = [vp]
+        lib.b200_hgemm_release.argtypes = []
         lib.b200_hgemm_launch_count.restype = ctypes.c_ulonglong
         lib.b200_hgemm_strerror.argtypes = [i]
         lib.b200_hgemm_strerror.restype = ctypes.c_char_p
@@ -80,7 +82,7 @@ def exported_symbols() -> dict[str, list[str]]:
             "b200_hgemm_f32acc", "b200_hgemm_f16acc", "b200_hgemm_num_configs", "b200_hgemm_config_info",
             "b200_hgemm_config_cluster", "b200_hgemm_config_m_rep",
             "b200_hgemm_select_config", "b200_hgemm_select", "b200_hgemm_run_config", "b200_hgemm_host", "b200_hgemm_launch_count",
-            "b200_hgemm_strerror", "b200_hgemm_schedule_units",
+            "b200_hgemm_strerror", "b200_hgemm_schedule_units", "b200_hgemm_prewarm", "b200_hgemm_release",
         ],
         "libb200_baselines.so": [
             "b200_bl_init", "b200_bl_destroy", "b200_bl_cublas", "b200_bl_lt_heuristic", "b200_bl_lt_autotune_find",
@@ -192,6 +194,16 @@ def schedule(config_id: int, m: int, n: int, k: int, splits: int = 1, num_sms: i
             cnt = lib.b200_hgemm_schedule_units(config_id, m, n, k, splits, num_sms, w, buf, cap, None, None, contrib)
         units.append([(buf[3 * j], buf[3 * j + 1], buf[3 * j + 2], contrib[j]) for j in range(cnt)])
     return {"workers": nw.value, "sk_tiles": sk.value, "units": units}
+
+
+def prewarm(stream: int | None = None) -> None:
+    """Allocate the split-K / stream-K scratch of (current device, stream) now — needed before a CUDA-graph capture."""
+    _check(hgemm_lib().b200_hgemm_prewarm(stream), "b200_hgemm_prewarm")
+
+
+def release() -> None:
+    """Free every device allocation the library holds (scratch, host-entry staging). Nothing may be in flight."""
+    _check(hgemm_lib().b200_hgemm_release(), "b200_hgemm_release")
 
 
 def launch_count() -> int:

@@ -4,6 +4,9 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 
 #include "hgemm_configs.cuh"
 #include "hgemm_dispatch.cuh"
@@ -60,6 +63,22 @@ int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int
   if (acc_bits == 32) return run_config<true>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
   if (acc_bits == 16) return run_config<false>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
   return b200::host::kBadConfig;
+}
+
+constexpr int kHostBlocks = 4;   // row blocks of the pipelined host entry
+struct HostCtx {
+  std::mutex mu;
+  void* dbuf = nullptr; size_t dcap = 0;
+  cudaStream_t in = nullptr, run = nullptr, out = nullptr;
+  cudaEvent_t b_in = nullptr, a_in[kHostBlocks] = {}, done[kHostBlocks] = {};
+};
+std::mutex g_host_mu;
+std::map<int, std::unique_ptr<HostCtx>> g_host_ctx;
+HostCtx& host_ctx(int dev) {
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  auto& slot = g_host_ctx[dev];
+  if (!slot) slot.reset(new HostCtx());
+  return *slot;
 }
 
 }  // namespace
@@ -164,33 +183,35 @@ int b200_hgemm_f16acc(const void* A, const void* /*B_rowmajor*/, const void* B_k
 int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* hC, int M, int N, int K) {
   if (!hA || !hB_kmajor || !hC) return b200::host::kNullPointer;
   if (M <= 0 || N <= 0 || K <= 0) return b200::host::kBadShape;
-  // device scratch grows monotonically and is reused across calls
-  static thread_local void* dbuf = nullptr;
-  static thread_local size_t dcap = 0;
+  if (acc_bits != 32 && acc_bits != 16) return b200::host::kBadConfig;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return int(e);
+  // Per-device context (device scratch that grows monotonically, three private streams and their events), created on
+  // first use, shared by all host threads and freed by b200_hgemm_release(). The call is synchronous, so callers on
+  // one device take turns (ctx.mu); callers on different devices do not meet.
+  HostCtx& ctx = host_ctx(dev);
+  std::lock_guard<std::mutex> turn(ctx.mu);
   const size_t a_bytes = size_t(M) * K * 2, b_bytes = size_t(N) * K * 2, c_bytes = size_t(M) * N * 2;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   const size_t need = up(a_bytes) + up(b_bytes) + up(c_bytes);
-  if (need > dcap) {
-    if (dbuf) cudaFree(dbuf);
-    dbuf = nullptr; dcap = 0;
-    cudaError_t e = cudaMalloc(&dbuf, need);
-    if (e != cudaSuccess) return int(e);
-    dcap = need;
+  if (need > ctx.dcap) {
+    if (ctx.dbuf) cudaFree(ctx.dbuf);
+    ctx.dbuf = nullptr; ctx.dcap = 0;
+    if ((e = cudaMalloc(&ctx.dbuf, need)) != cudaSuccess) return int(e);
+    ctx.dcap = need;
   }
-  char* dA = static_cast<char*>(dbuf);
+  char* dA = static_cast<char*>(ctx.dbuf);
   char* dB = dA + up(a_bytes);
   char* dC = dB + up(b_bytes);
-  if (acc_bits != 32 && acc_bits != 16) return b200::host::kBadConfig;
   auto gemm = [&](const void* a, void* c, int m, cudaStream_t s) {
     return acc_bits == 32 ? b200_hgemm_f32acc(a, nullptr, dB, c, m, N, K, s) : b200_hgemm_f16acc(a, nullptr, dB, c, m, N, K, s);
   };
-  cudaError_t e;
 
   // Large problems are PCIe time: B goes first, then A in row blocks; the GEMM of block i runs while block i+1 is on
   // its way in and block i-1 on its way out (PCIe is full duplex), on three private streams joined before returning.
   // Row blocks are independent GEMMs (C_i = A_i * B), so the result does not depend on the blocking.
-  constexpr int kBlocks = 4;
-  const bool pipelined = M >= kBlocks * 256 && (a_bytes + c_bytes) >= (size_t(8) << 20) &&
+  const bool pipelined = M >= kHostBlocks * 256 && (a_bytes + c_bytes) >= (size_t(8) << 20) &&
                          !(std::getenv("B200_HGEMM_HOST_UNPIPELINED"));
   if (!pipelined) {
     if ((e = cudaMemcpyAsync(dA, hA, a_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess) return int(e);
@@ -202,40 +223,71 @@ int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* h
     return e == cudaSuccess ? 0 : int(e);
   }
 
-  struct Lanes { cudaStream_t in = nullptr, run = nullptr, out = nullptr; cudaEvent_t b_in = nullptr, a_in[kBlocks] = {}, done[kBlocks] = {}; };
-  static thread_local Lanes L;
-  if (!L.in) {
-    if ((e = cudaStreamCreateWithFlags(&L.in, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
-    if ((e = cudaStreamCreateWithFlags(&L.run, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
-    if ((e = cudaStreamCreateWithFlags(&L.out, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
-    if ((e = cudaEventCreateWithFlags(&L.b_in, cudaEventDisableTiming)) != cudaSuccess) return int(e);
-    for (int i = 0; i < kBlocks; ++i) {
-      if ((e = cudaEventCreateWithFlags(&L.a_in[i], cudaEventDisableTiming)) != cudaSuccess) return int(e);
-      if ((e = cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming)) != cudaSuccess) return int(e);
+  if (!ctx.in) {
+    if ((e = cudaStreamCreateWithFlags(&ctx.in, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx.run, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx.out, cudaStreamNonBlocking)) != cudaSuccess) return int(e);
+    if ((e = cudaEventCreateWithFlags(&ctx.b_in, cudaEventDisableTiming)) != cudaSuccess) return int(e);
+    for (int i = 0; i < kHostBlocks; ++i) {
+      if ((e = cudaEventCreateWithFlags(&ctx.a_in[i], cudaEventDisableTiming)) != cudaSuccess) return int(e);
+      if ((e = cudaEventCreateWithFlags(&ctx.done[i], cudaEventDisableTiming)) != cudaSuccess) return int(e);
     }
   }
   // work queued by the caller on the legacy default stream (non-blocking streams do not wait for it on their own)
   if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return int(e);
-  if ((e = cudaMemcpyAsync(dB, hB_kmajor, b_bytes, cudaMemcpyHostToDevice, L.in)) != cudaSuccess) return int(e);
-  if ((e = cudaEventRecord(L.b_in, L.in)) != cudaSuccess) return int(e);
-  if ((e = cudaStreamWaitEvent(L.run, L.b_in, 0)) != cudaSuccess) return int(e);
-  const int rows_per = ((M + kBlocks - 1) / kBlocks + 127) / 128 * 128;   // whole 128-row tiles per block
-  for (int i = 0; i < kBlocks; ++i) {
+  // A's first block leaves before B so that the link is busy from the first microsecond; the first GEMM needs both
+  const int rows_per = ((M + kHostBlocks - 1) / kHostBlocks + 127) / 128 * 128;   // whole 128-row tiles per block
+  if ((e = cudaMemcpyAsync(dB, hB_kmajor, b_bytes, cudaMemcpyHostToDevice, ctx.in)) != cudaSuccess) return int(e);
+  if ((e = cudaEventRecord(ctx.b_in, ctx.in)) != cudaSuccess) return int(e);
+  if ((e = cudaStreamWaitEvent(ctx.run, ctx.b_in, 0)) != cudaSuccess) return int(e);
+  for (int i = 0; i < kHostBlocks; ++i) {
     const int r0 = i * rows_per, rows = std::min(rows_per, M - r0);
     if (rows <= 0) break;
     const size_t a_off = size_t(r0) * K * 2, c_off = size_t(r0) * N * 2;
-    if ((e = cudaMemcpyAsync(dA + a_off, static_cast<const char*>(hA) + a_off, size_t(rows) * K * 2, cudaMemcpyHostToDevice, L.in)) != cudaSuccess) return int(e);
-    if ((e = cudaEventRecord(L.a_in[i], L.in)) != cudaSuccess) return int(e);
-    if ((e = cudaStreamWaitEvent(L.run, L.a_in[i], 0)) != cudaSuccess) return int(e);
-    int st = gemm(dA + a_off, dC + c_off, rows, L.run);
+    if ((e = cudaMemcpyAsync(dA + a_off, static_cast<const char*>(hA) + a_off, size_t(rows) * K * 2, cudaMemcpyHostToDevice, ctx.in)) != cudaSuccess) return int(e);
+    if ((e = cudaEventRecord(ctx.a_in[i], ctx.in)) != cudaSuccess) return int(e);
+    if ((e = cudaStreamWaitEvent(ctx.run, ctx.a_in[i], 0)) != cudaSuccess) return int(e);
+    int st = gemm(dA + a_off, dC + c_off, rows, ctx.run);
     if (st) { cudaDeviceSynchronize(); return st; }
-    if ((e = cudaEventRecord(L.done[i], L.run)) != cudaSuccess) return int(e);
-    if ((e = cudaStreamWaitEvent(L.out, L.done[i], 0)) != cudaSuccess) return int(e);
-    if ((e = cudaMemcpyAsync(static_cast<char*>(hC) + c_off, dC + c_off, size_t(rows) * N * 2, cudaMemcpyDeviceToHost, L.out)) != cudaSuccess) return int(e);
+    if ((e = cudaEventRecord(ctx.done[i], ctx.run)) != cudaSuccess) return int(e);
+    if ((e = cudaStreamWaitEvent(ctx.out, ctx.done[i], 0)) != cudaSuccess) return int(e);
+    if ((e = cudaMemcpyAsync(static_cast<char*>(hC) + c_off, dC + c_off, size_t(rows) * N * 2, cudaMemcpyDeviceToHost, ctx.out)) != cudaSuccess) return int(e);
   }
-  if ((e = cudaStreamSynchronize(L.out)) != cudaSuccess) return int(e);   // the last copy out is behind everything else
-  if ((e = cudaStreamSynchronize(L.run)) != cudaSuccess) return int(e);
-  e = cudaStreamSynchronize(L.in);
+  if ((e = cudaStreamSynchronize(ctx.out)) != cudaSuccess) return int(e);   // the last copy out is behind everything else
+  if ((e = cudaStreamSynchronize(ctx.run)) != cudaSuccess) return int(e);
+  e = cudaStreamSynchronize(ctx.in);
+  return e == cudaSuccess ? 0 : int(e);
+}
+
+int b200_hgemm_prewarm(void* stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return int(e);
+  b200::host::SplitKScratch* sk = nullptr;
+  return b200::host::splitk_scratch(dev, static_cast<cudaStream_t>(stream), &sk);
+}
+
+int b200_hgemm_release(void) {
+  b200::host::release_scratch();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  for (auto& kv : g_host_ctx) {
+    HostCtx& c = *kv.second;
+    std::lock_guard<std::mutex> turn(c.mu);
+    cudaSetDevice(kv.first);
+    cudaDeviceSynchronize();
+    if (c.dbuf) cudaFree(c.dbuf);
+    c.dbuf = nullptr; c.dcap = 0;
+    if (c.in) {
+      cudaStreamDestroy(c.in); cudaStreamDestroy(c.run); cudaStreamDestroy(c.out);
+      cudaEventDestroy(c.b_in);
+      for (int i = 0; i < kHostBlocks; ++i) { cudaEventDestroy(c.a_in[i]); cudaEventDestroy(c.done[i]); }
+      c.in = c.run = c.out = nullptr;
+    }
+  }
+  cudaSetDevice(cur);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : int(e);
 }
 

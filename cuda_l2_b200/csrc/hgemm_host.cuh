@@ -9,6 +9,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <deque>
+#include <mutex>
 
 #include "hgemm_sm100.cuh"
 
@@ -24,6 +26,7 @@ enum Status : int {
   kNullPointer = -5,
   kBadConfig = -6,
   kNotBlackwell = -7,
+  kNoScratch = -8,       // internal: no split-K scratch for this (device, stream) and none can be allocated now (stream capture)
   // > 0: a cudaError_t from the launch
 };
 
@@ -37,6 +40,7 @@ inline const char* status_string(int s) {
     case kNullPointer: return "null operand pointer";
     case kBadConfig: return "unknown kernel configuration id";
     case kNotBlackwell: return "device is not compute capability 10.x (sm_100a build)";
+    case kNoScratch: return "split-K scratch unavailable (allocate it outside stream capture with b200_hgemm_prewarm)";
     default: return s > 0 ? cudaGetErrorString(static_cast<cudaError_t>(s)) : "unknown error";
   }
 }
@@ -142,32 +146,63 @@ inline int validate(const void* A, const void* Bt, const void* C, int M, int N, 
   return kOk;
 }
 
-// Split-K scratch: fp32 partial tiles + arrival counters, allocated on first use (one per device and
-// stream; a handful of streams at most) and kept for the life of the process. Counters are zero between
-// launches (the kernel resets them), so consecutive launches on a stream need no host-side clearing.
+// Split-K / stream-K scratch: fp32 partial tiles + arrival counters, one per (device, stream), allocated on first use
+// (or ahead of time by b200_hgemm_prewarm — required before a CUDA-graph capture, where cudaMalloc is illegal) and kept
+// until b200_hgemm_release(). Process-wide and mutex-protected: any host thread that launches on a (device, stream)
+// finds the same scratch, and the pool grows with the number of streams instead of silently running out. Counters are
+// zero between launches (the kernel resets them), so consecutive launches on a stream need no host-side clearing.
+// Launches that share a scratch must be ordered by their stream — which they are, being on the same stream.
 struct SplitKScratch {
   int dev = -1; cudaStream_t stream = nullptr; float* ws = nullptr; unsigned* ctr = nullptr;
 };
 constexpr size_t kSplitKWsBytes = size_t(kMaxStreamKSlots) * kBlockM * 256 * sizeof(float);   // 160 units of 128x256 fp32
 // split-K arrive/done counters, then one stream-K flag per (CTA slot, epilogue warp)
 constexpr size_t kSplitKCtrBytes = (2 * kMaxSplitTiles + kMaxStreamKSlots * kStreamKFlagsPerSlot) * sizeof(unsigned);
+struct ScratchPool {
+  std::mutex mu;
+  std::deque<SplitKScratch> entries;   // deque: growing never moves an entry another thread holds a pointer to
+};
+inline ScratchPool& scratch_pool() {
+  static ScratchPool pool;
+  return pool;
+}
 inline int splitk_scratch(int dev, cudaStream_t stream, SplitKScratch** out) {
-  static thread_local SplitKScratch pool[8];
-  SplitKScratch* free_slot = nullptr;
-  for (auto& e : pool) {
+  ScratchPool& pool = scratch_pool();
+  std::lock_guard<std::mutex> lock(pool.mu);
+  for (auto& e : pool.entries)
     if (e.ws && e.dev == dev && e.stream == stream) { *out = &e; return kOk; }
-    if (!e.ws && !free_slot) free_slot = &e;
-  }
-  if (!free_slot) return kBadConfig;
-  cudaError_t err = cudaMalloc(&free_slot->ws, kSplitKWsBytes);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); return kNoScratch; }
+  if (cap != cudaStreamCaptureStatusNone) return kNoScratch;   // cudaMalloc would invalidate the capture
+  SplitKScratch e;
+  cudaError_t err = cudaMalloc(&e.ws, kSplitKWsBytes);
   if (err != cudaSuccess) return int(err);
-  err = cudaMalloc(&free_slot->ctr, kSplitKCtrBytes);
-  if (err != cudaSuccess) { cudaFree(free_slot->ws); free_slot->ws = nullptr; return int(err); }
-  err = cudaMemsetAsync(free_slot->ctr, 0, kSplitKCtrBytes, stream);
-  if (err != cudaSuccess) return int(err);
-  free_slot->dev = dev; free_slot->stream = stream;
-  *out = free_slot;
+  err = cudaMalloc(&e.ctr, kSplitKCtrBytes);
+  if (err != cudaSuccess) { cudaFree(e.ws); return int(err); }
+  err = cudaMemsetAsync(e.ctr, 0, kSplitKCtrBytes, stream);
+  if (err != cudaSuccess) { cudaFree(e.ws); cudaFree(e.ctr); return int(err); }
+  e.dev = dev; e.stream = stream;
+  SplitKScratch* slot = nullptr;
+  for (auto& old : pool.entries) if (!old.ws) { slot = &old; break; }   // reuse a released entry
+  if (slot) *slot = e; else { pool.entries.push_back(e); slot = &pool.entries.back(); }
+  *out = slot;
   return kOk;
+}
+// Frees every scratch allocation of this process (all devices). The caller guarantees that no launch of this
+// library is in flight or issued concurrently.
+inline void release_scratch() {
+  ScratchPool& pool = scratch_pool();
+  std::lock_guard<std::mutex> lock(pool.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& e : pool.entries) {
+    if (!e.ws) continue;
+    cudaSetDevice(e.dev);
+    cudaDeviceSynchronize();
+    cudaFree(e.ws); cudaFree(e.ctr);
+    e = SplitKScratch{};
+  }
+  cudaSetDevice(cur);
 }
 
 // Largest usable split factor for this problem/config: units must fit the SMs (one CTA per unit), every
@@ -265,6 +300,12 @@ int max_resident_clusters(const DeviceInfo& di) {
   return max_clusters;
 }
 
+// B200_HGEMM_NO_COOPERATIVE=1 launches the co-resident K-modes as ordinary grids (developer A/B of the launch cost).
+inline bool cooperative_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200_HGEMM_NO_COOPERATIVE"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 // One (configuration, K-mode) instance of the kernel: opt into its dynamic shared memory once, then launch.
 // Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this template
 // (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be merged across
@@ -297,13 +338,27 @@ int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
   cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = unsigned(cluster);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = unsigned(cluster);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  // Workspace split-K and stream-K CTAs wait for sibling CTAs of the same grid (arrival counters / flags in global
+  // memory), so the whole grid must be resident at once. A cooperative launch makes that the driver's guarantee: the
+  // grid starts only when all of it fits (other kernels holding SMs delay it instead of starving half of it into
+  // the watchdog), and a grid that can never fit is refused with cudaErrorCooperativeLaunchTooLarge, which launch()
+  // turns into the undivided schedule. (Cluster split-K needs nothing: a cluster is co-scheduled by the hardware.)
+  if ((KMODE == kWorkspaceSplitK || KMODE == kStreamK) && cooperative_enabled()) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg, KMODE>, a.ma, a.mb, a.mc, a.M, a.N, a.K, a.group_m,
                                      a.plan.splits, a.plan.sk_tiles, a.ws, a.ctr, a.c, a.hint_a, a.hint_b);
   return e == cudaSuccess ? kOk : int(e);
@@ -348,7 +403,7 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
       a.ws = sk->ws; a.ctr = sk->ctr;
     } else {
       cudaGetLastError();
-      a.plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed / more than 8 streams): run undivided
+      a.plan = make_plan<Cfg>(M, N, K, workers, 1);   // no scratch (allocation failed, or first use inside a stream capture): run undivided
     }
   }
   a.M = M; a.N = N; a.K = K;
@@ -365,14 +420,21 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
     if (a_bytes >= kStream && b_bytes <= kL2Keep && n_tiles <= 4) { a.hint_a = ptx::kL2EvictFirst; a.hint_b = ptx::kL2EvictLast; }
     else if (b_bytes >= kStream && a_bytes <= kL2Keep && m_tiles <= 4) { a.hint_b = ptx::kL2EvictFirst; a.hint_a = ptx::kL2EvictLast; }
   }
+  // a co-resident mode the device cannot hold (refused before anything ran) falls back to the undivided schedule
+  auto undivided = [&](int err) {
+    if (err != int(cudaErrorCooperativeLaunchTooLarge) && err != int(cudaErrorLaunchOutOfResources)) return err;
+    cudaGetLastError();
+    a.plan = make_plan<Cfg>(M, N, K, workers, 1);
+    return launch_mode<Cfg, kPlain>(di, a);
+  };
   if constexpr (kCanStream) {
-    if (a.plan.sk_tiles > 0) return launch_mode<Cfg, kStreamK>(di, a);
+    if (a.plan.sk_tiles > 0) return undivided(launch_mode<Cfg, kStreamK>(di, a));
   }
   if constexpr (Cfg::SPLIT_K && (MODES & (1u << kClusterSplitK))) {
     if (a.plan.cluster_reduce) return launch_mode<Cfg, kClusterSplitK>(di, a);
   }
   if constexpr (Cfg::SPLIT_K && (MODES & (1u << kWorkspaceSplitK))) {
-    if (a.plan.splits > 1) return launch_mode<Cfg, kWorkspaceSplitK>(di, a);
+    if (a.plan.splits > 1) return undivided(launch_mode<Cfg, kWorkspaceSplitK>(di, a));
   }
   return launch_mode<Cfg, kPlain>(di, a);
 }

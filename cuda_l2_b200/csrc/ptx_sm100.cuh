@@ -351,12 +351,13 @@ __device__ __forceinline__ void st_shared_v4f(uint32_t addr, float a, float b, f
 }
 __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  // reads data published by an mbarrier wait (async-proxy bulk copies): must not be hoisted above it
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {

@@ -52,6 +52,11 @@ def partition(shapes, world: int) -> list[list[tuple[int, int, int]]]:
     return parts
 
 
+def _flops(mnk: str) -> float:
+    m, n, k = (int(x) for x in mnk.split("_"))
+    return 2.0 * m * n * k
+
+
 def speedup_row(mnk: str, tf: dict) -> dict:
     """One row of the reference's CSV schema from absolute TFLOP/s (ours + baselines); "-max" is the harder
     of the two layouts, i.e. the smaller speed-up (summarize_result.py:43-53)."""
@@ -254,5 +259,5 @@ def write_reports(records: list[dict], out_csv: Path, peak_tflops: float, peak_g
             "won_vs_cublas_max": sum(r["ours"] >= max(r["cublas_tn"], r["cublas_nn"]) for r in ok),
             "won_vs_lt_heuristic_max": sum(r["ours"] >= max(r["lt_heur_tn"], r["lt_heur_nn"]) for r in ok),
             "won_vs_lt_auto_max": wins, "win_fraction": wins / n if n else float("nan"), "mean_speedup_vs_lt_auto_max": mean,
-            "aggregate_tflops": sum(2.0 * eval(r["mnk"].replace("_", "*")) for r in ok) /
-                                sum(2.0 * eval(r["mnk"].replace("_", "*")) / (r["ours"] * 1e12) for r in ok) * 1e-12 if n else 0.0}
+            "aggregate_tflops": (sum(_flops(r["mnk"]) for r in ok) /
+                                 sum(_flops(r["mnk"]) / (r["ours"] * 1e12) for r in ok) * 1e-12) if n else 0.0}

@@ -79,6 +79,20 @@ int b200_hgemm_schedule_units(int config_id, int M, int N, int K, int splits, in
  * (benchmarking_utils.py:12-33, which also brackets one call with device synchronisation). */
 int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* hC, int M, int N, int K);
 
+/* Resource management. The library keeps, per (device, stream) that ever ran a workspace split-K or stream-K launch,
+ * 21 MB of device scratch (first use allocates with cudaMalloc — illegal inside a CUDA-graph capture, where the launch
+ * then quietly runs the undivided schedule instead), and per device the staging buffers / streams of b200_hgemm_host.
+ * The reference kernels allocate such state per call (torch::zeros scratch, kernels/a100_F32F16F16F32/64_256_16384.cu:233-248;
+ * cudaMalloc of the CUTLASS workspace, kernels/h100_F32F16F16F32/4096_4096_4096.cu:148-149).
+ *   b200_hgemm_prewarm(stream)  allocate the scratch of (current device, stream) now — call it before capturing a graph;
+ *   b200_hgemm_release()        free everything the library holds on every device. No launch of this library may be
+ *                               in flight or issued concurrently. Later calls re-allocate on demand.
+ * Both return 0 or a status / cudaError_t.
+ * Split-K / stream-K launches wait for sibling CTAs of their own grid; they are launched cooperatively, so the driver
+ * starts such a grid only when all of it fits on the device (it may therefore wait for other kernels to drain). */
+int b200_hgemm_prewarm(void* stream);
+int b200_hgemm_release(void);
+
 /* Kernel launches issued by this library since load (the bench's `gpu_launches` evidence). */
 unsigned long long b200_hgemm_launch_count(void);
 
