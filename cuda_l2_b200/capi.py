@@ -39,6 +39,9 @@ def hgemm_lib() -> ctypes.CDLL:
         for fn in ("b200_hgemm_f32acc", "b200_hgemm_f16acc"):
             getattr(lib, fn).argtypes = [vp, vp, vp, vp, i, i, i, vp]
             getattr(lib, fn).restype = i
+        lib.b200_bgemm_f32acc.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        lib.b200_bgemm_f32acc.restype = i
+        lib.b200_bgemm_run_config.argtypes = [i, vp, vp, vp, i, i, i, i, i, i, vp]
         lib.b200_hgemm_num_configs.restype = i
         lib.b200_hgemm_config_info.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.b200_hgemm_config_cluster.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(i)]
@@ -83,6 +86,7 @@ def exported_symbols() -> dict[str, list[str]]:
             "b200_hgemm_config_cluster", "b200_hgemm_config_m_rep",
             "b200_hgemm_select_config", "b200_hgemm_select", "b200_hgemm_run_config", "b200_hgemm_host", "b200_hgemm_launch_count",
             "b200_hgemm_strerror", "b200_hgemm_schedule_units", "b200_hgemm_prewarm", "b200_hgemm_release",
+            "b200_bgemm_f32acc", "b200_bgemm_run_config",
         ],
         "libb200_baselines.so": [
             "b200_bl_init", "b200_bl_destroy", "b200_bl_cublas", "b200_bl_lt_heuristic", "b200_bl_lt_autotune_find",
@@ -125,6 +129,38 @@ def hgemm(a, b_col_major, c, acc: str | int = "fp32", stream: int | None = None)
     bits = ACC_BITS[acc]
     fn = hgemm_lib().b200_hgemm_f32acc if bits == 32 else hgemm_lib().b200_hgemm_f16acc
     _check(fn(a.data_ptr(), None, b_col_major.data_ptr(), c.data_ptr(), m, n, k, stream), "b200_hgemm")
+
+
+def gemm_kmajor(a, b_kmajor, c, acc: str | int = "fp32", stream: int | None = None, config_id: int | None = None,
+                group_m: int = 0, splits: int = 1) -> None:
+    """c[M,N] = a[M,K] @ b_kmajor[N,K]^T with the operands' dtype deciding the kernel family: fp16 (fp32 or fp16
+    accumulation) or bf16 (fp32 accumulation). ``b_kmajor`` is shaped as stored, [N,K] — an ``nn.Linear`` weight.
+    ``config_id`` pins one kernel configuration (tests); default is the dispatcher."""
+    import torch
+
+    if a.dtype not in (torch.half, torch.bfloat16) or b_kmajor.dtype != a.dtype or c.dtype != a.dtype:
+        raise B200HgemmError(f"operands must all be fp16 or all bf16, got {a.dtype}, {b_kmajor.dtype}, {c.dtype}")
+    for name, t in (("a", a), ("b_kmajor", b_kmajor), ("c", c)):
+        if not t.is_cuda or not t.is_contiguous():
+            raise B200HgemmError(f"{name} must be a contiguous CUDA tensor")
+    (m, k), (n, k2) = a.shape, b_kmajor.shape
+    if k2 != k or tuple(c.shape) != (m, n):
+        raise B200HgemmError(f"shape mismatch: a {tuple(a.shape)}, b_kmajor {tuple(b_kmajor.shape)}, c {tuple(c.shape)}")
+    lib = hgemm_lib()
+    bits = ACC_BITS[acc]
+    if a.dtype == torch.bfloat16:
+        if bits != 32:
+            raise B200HgemmError("bf16 operands accumulate in fp32 only")
+        if config_id is None:
+            st = lib.b200_bgemm_f32acc(a.data_ptr(), None, b_kmajor.data_ptr(), c.data_ptr(), m, n, k, stream)
+        else:
+            st = lib.b200_bgemm_run_config(config_id, a.data_ptr(), b_kmajor.data_ptr(), c.data_ptr(), m, n, k, group_m, 0, splits, stream)
+    elif config_id is None:
+        fn = lib.b200_hgemm_f32acc if bits == 32 else lib.b200_hgemm_f16acc
+        st = fn(a.data_ptr(), None, b_kmajor.data_ptr(), c.data_ptr(), m, n, k, stream)
+    else:
+        st = lib.b200_hgemm_run_config(bits, config_id, a.data_ptr(), b_kmajor.data_ptr(), c.data_ptr(), m, n, k, group_m, 0, splits, stream)
+    _check(st, "b200 gemm")
 
 
 def hgemm_config(a, b_col_major, c, config_id: int, acc: str | int = "fp32", group_m: int = 0, max_ctas: int = 0,

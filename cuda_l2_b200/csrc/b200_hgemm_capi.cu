@@ -14,8 +14,9 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+constexpr int kBf16Acc32 = 0xB32;   // internal selector of run(): bf16 operands, fp32 accumulation
 
-template <bool kAccF32>
+template <bool kAccF32, bool kBf16 = false>
 int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int K, int group_m, int max_ctas,
                int splits, cudaStream_t s) {
   using namespace b200;
@@ -23,7 +24,7 @@ int run_config(int id, const void* A, const void* Bt, void* C, int M, int N, int
   switch (id) {
 #define B200_CASE(ID, BN, STAGES, CG, CM, CN, MR)                                                      \
   case ID:                                                                                         \
-    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN, MR>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
+    st = host::launch<Config<BN, STAGES, CG, kAccF32, CM, CN, MR, kBf16>>(A, Bt, C, M, N, K, s, group_m, max_ctas, splits); \
     break;
     B200_HGEMM_CONFIGS(B200_CASE)
 #undef B200_CASE
@@ -62,6 +63,7 @@ int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (acc_bits == 32) return run_config<true>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
   if (acc_bits == 16) return run_config<false>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
+  if (acc_bits == kBf16Acc32) return run_config<true, true>(id, A, Bt, C, M, N, K, group_m, max_ctas, splits, s);
   return b200::host::kBadConfig;
 }
 
@@ -178,6 +180,20 @@ int b200_hgemm_f16acc(const void* A, const void* /*B_rowmajor*/, const void* B_k
   if (st) return st;
   const b200::dispatch::Choice ch = b200::dispatch::select(16, M, N, K);
   return run(16, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, ch.splits, stream);
+}
+
+int b200_bgemm_f32acc(const void* A, const void* /*B_rowmajor*/, const void* B_kmajor, void* C, int M, int N,
+                      int K, void* stream) {
+  int st = b200::host::validate(A, B_kmajor, C, M, N, K);
+  if (st) return st;
+  // same data movement and the same MMA rate as the fp16 / fp32-accumulate kernel: its tuned table applies
+  const b200::dispatch::Choice ch = b200::dispatch::select(32, M, N, K);
+  return run(kBf16Acc32, ch.config_id, A, B_kmajor, C, M, N, K, ch.group_m, 0, ch.splits, stream);
+}
+
+int b200_bgemm_run_config(int config_id, const void* A, const void* B_kmajor, void* C, int M, int N, int K,
+                          int group_m, int max_ctas, int splits, void* stream) {
+  return run(kBf16Acc32, config_id, A, B_kmajor, C, M, N, K, group_m, max_ctas, splits, stream);
 }
 
 int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* hC, int M, int N, int K) {

@@ -5,7 +5,8 @@
 //   dev_check time  <acc_bits> <cfg|-1> <M> <N> <K> [iters gm splits]  CUDA-event timing (+ cuBLAS for scale)
 //   dev_check sustain <acc_bits> <cfg|-1> <M> <N> <K> [seconds gm splits]   burst vs power-capped throughput, ours and cuBLAS
 //   dev_check sweep <acc_bits> <M> <N> <K> [iters]           time every config and group_m variant
-//   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  harness metric vs 6 library baselines
+//   dev_check wall  <acc_bits> <M> <N> <K> [seconds [tune_warm tune_bench]]  the harness's protocol (one baseline/ours pair at a time,
+//                                                     fresh operands per iteration, zero-filled output) vs 6 library baselines
 //   dev_check wallgrid <acc_bits> <part> <nparts> [seconds tune_warm tune_bench limit]   `wall` over a share of the grid
 //   dev_check_trace trace <acc_bits> <cfg|-1> <M> <N> <K> [gm splits cold]   per-CTA phase timestamps of one launch (trace build only)
 //   dev_check grid  <acc_bits> [part nparts budget_ms min_gflop max_gflop [wall]]  time every config on the whole shape grid (CSV);
@@ -54,6 +55,30 @@ __global__ void fill_normalish(__half* p, size_t n, uint32_t seed) {
   uint32_t x = uint32_t(i) * 2654435761u ^ seed;
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   p[i] = __float2half((float(x & 0xffff) / 65536.f - 0.5f) * 2.f);
+}
+// N(0,1) like the harness's torch.randn(...).half() operands (Box-Muller on a counter hash; benchmarking_utils.py:36-37)
+__global__ void fill_randn(__half* p, size_t n, uint32_t seed) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = uint32_t(i) * 2654435761u ^ seed, y = uint32_t(i >> 32) * 0x9E3779B9u + uint32_t(i) * 0x85ebca6bu + ~seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  y ^= y >> 16; y *= 0x7feb352du; y ^= y >> 15; y *= 0x846ca68bu; y ^= y >> 16;
+  const float u1 = (float(x >> 8) + 1.0f) * (1.0f / 16777217.0f), u2 = float(y >> 8) * (1.0f / 16777216.0f);
+  p[i] = __float2half(sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2));
+}
+// row-major [R,C] -> row-major [C,R] (tools/utils.py:110-115 as_col_major on the device, for the harness protocol)
+__global__ void transpose_rc(const __half* __restrict__ in, __half* __restrict__ out, int R, int C) {
+  __shared__ __half tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = in[size_t(r) * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[size_t(c) * R + r] = tile[threadIdx.x][j];
+  }
 }
 __global__ void fill_u16(uint16_t* p, size_t n, uint16_t v) {
   size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
@@ -545,18 +570,40 @@ static int do_trace(int acc, int cfg, int M, int N, int K, int gm, int splits, i
 }
 #endif
 
-// wall: the harness metric in C++ — host wall clock around ONE call bracketed by device synchronisation
-// (reference benchmarking_utils.py:23-31), mean of per-sample TFLOP/s, our dispatcher against the six library
-// baselines (cuBLASLt auto-tuning runs the reference's 50 + 100 round search first unless rounds are given).
-static int wall_one(int acc, const Problem& p, const __half* Brow, double seconds, int tune_warm, int tune_bench) {
-  const int M = p.M, N = p.N, K = p.K;
+// wall: the harness's measurement PROTOCOL in C++ (reference benchmarking_offline.py:119-161, benchmarking_utils.py:12-69;
+// eval_one_file.sh:71-135), one (baseline, ours) pair at a time as the reference runs one pair per process:
+//   per pair     warm-up loop in the fixed order [baseline, ours], then the timed loop with the order shuffled per iteration;
+//   per iteration  fresh N(0,1) A [M,K] and B [K,N]; every function gets ITS OWN copies (a clone of A, a clone of B, the
+//                K-major transpose of B) and its own output filled with noise; device sync;
+//   per call     the output is zero-filled, device sync, host clock, ONE call, device sync, host clock;
+//   metric       mean over iterations of 2MNK / t per function; speed-up of a pair = ours / baseline FROM THAT PAIR;
+//                "-max" = the harder layout = the smaller speed-up (summarize_result.py:43-53).
+// cuBLASLt auto-tuning first runs the reference's search (50 warm-up + 100 timed rounds over every candidate the heuristic
+// returns) unless other round counts are given. `seconds` is the timed loop of each auto-tuning pair; the four pairs
+// that only fill the other CSV columns get 40 % of it. The pairs run in shuffled order.
+struct WallBuffers {   // sized once for the largest problem of a run
+  __half *A0, *B0;                 // this iteration's operands
+  __half *A[2], *Brow[2], *Bt[2], *C[2];   // [0] baseline's copies, [1] ours
+  void alloc(size_t maxe) {
+    CK(cudaMalloc(&A0, maxe * 2)); CK(cudaMalloc(&B0, maxe * 2));
+    for (int f = 0; f < 2; ++f) {
+      CK(cudaMalloc(&A[f], maxe * 2)); CK(cudaMalloc(&Brow[f], maxe * 2)); CK(cudaMalloc(&Bt[f], maxe * 2)); CK(cudaMalloc(&C[f], maxe * 2));
+    }
+  }
+  void release() {
+    cudaFree(A0); cudaFree(B0);
+    for (int f = 0; f < 2; ++f) { cudaFree(A[f]); cudaFree(Brow[f]); cudaFree(Bt[f]); cudaFree(C[f]); }
+  }
+};
+
+static int wall_one(int acc, int M, int N, int K, WallBuffers& w, double seconds, int tune_warm, int tune_bench) {
   int cand[2] = {0, 0}; float best_ms[2] = {0, 0};
   if (tune_warm < 0) {
-    // adaptive: the reference's 50 + 100 rounds where they are cheap, fewer rounds for long kernels so that
-    // the search stays near `-tune_warm` x 10 ms per layout (assuming ~40 candidates)
+    // adaptive: the reference's 50 + 100 rounds where they are cheap, fewer for long kernels so that the search of one
+    // layout stays near `-tune_warm` x 10 ms (8 candidates is what the heuristic returns on this library), never below 10 + 20
     const double est = std::max(std::max(2.0 * M * N * K / 1.2e15, 2.0 * (double(M) * K + double(N) * K + double(M) * N) / 5e12), 5e-6) + 8e-6;
     const double budget = -tune_warm * 0.01;
-    const int rounds = std::max(6, std::min(150, int(budget / (40.0 * est))));
+    const int rounds = std::max(30, std::min(150, int(budget / (8.0 * est))));
     tune_warm = rounds / 3; tune_bench = rounds - tune_warm;
   }
   for (int lay = 0; lay < 2; ++lay) {
@@ -564,98 +611,142 @@ static int wall_one(int acc, const Problem& p, const __half* Brow, double second
     if (st) { printf("WALLFAIL,%d,%d,%d,%d,autotune find status %d\n", acc, M, N, K, st); return 1; }
     b200_bl_lt_autotune_info(acc, lay, &cand[lay], &best_ms[lay]);
   }
-  struct Fn { const char* name; std::function<int()> f; };
-  std::vector<Fn> fns = {
-      {"ours", [&] { return run_ours(acc, -1, p); }},
-      {"cublas_tn", [&] { return b200_bl_cublas(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
-      {"cublas_nn", [&] { return b200_bl_cublas(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
-      {"lt_heur_tn", [&] { return b200_bl_lt_heuristic(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
-      {"lt_heur_nn", [&] { return b200_bl_lt_heuristic(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
-      {"lt_auto_tn", [&] { return b200_bl_lt_autotune(acc, 1, p.A, p.Bt, p.Cref, M, N, K); }},
-      {"lt_auto_nn", [&] { return b200_bl_lt_autotune(acc, 0, p.A, Brow, p.Cref, M, N, K); }},
+  // baseline f(copies index 0); ours always works on copies index 1
+  struct Fn { const char* name; bool primary; std::function<int()> f; };
+  std::vector<Fn> base = {
+      {"cublas_tn", false, [&] { return b200_bl_cublas(acc, 1, w.A[0], w.Bt[0], w.C[0], M, N, K); }},
+      {"cublas_nn", false, [&] { return b200_bl_cublas(acc, 0, w.A[0], w.Brow[0], w.C[0], M, N, K); }},
+      {"lt_heur_tn", false, [&] { return b200_bl_lt_heuristic(acc, 1, w.A[0], w.Bt[0], w.C[0], M, N, K); }},
+      {"lt_heur_nn", false, [&] { return b200_bl_lt_heuristic(acc, 0, w.A[0], w.Brow[0], w.C[0], M, N, K); }},
+      {"lt_auto_tn", true, [&] { return b200_bl_lt_autotune(acc, 1, w.A[0], w.Bt[0], w.C[0], M, N, K); }},
+      {"lt_auto_nn", true, [&] { return b200_bl_lt_autotune(acc, 0, w.A[0], w.Brow[0], w.C[0], M, N, K); }},
   };
+  auto ours = [&] {
+    return acc == 32 ? b200_hgemm_f32acc(w.A[1], w.Brow[1], w.Bt[1], w.C[1], M, N, K, nullptr)
+                     : b200_hgemm_f16acc(w.A[1], w.Brow[1], w.Bt[1], w.C[1], M, N, K, nullptr);
+  };
+  const size_t ea = size_t(M) * K, eb = size_t(K) * N, ec = size_t(M) * N;
   const double flops = 2.0 * M * N * K;
-  std::vector<double> sum_tf(fns.size(), 0.0), sum_ms(fns.size(), 0.0), sum_call_ms(fns.size(), 0.0);
-  std::vector<int> order(fns.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
-  std::mt19937 rng(12345);
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  for (auto& fn : fns) { if (fn.f()) { printf("WALLFAIL,%d,%d,%d,%d,warm-up call failed: %s\n", acc, M, N, K, fn.name); return 1; } }
-  CK(cudaDeviceSynchronize());
-  int samples = 0;
-  const auto t_begin = now();
-  const auto t_warm = t_begin + std::chrono::duration<double>(seconds * 0.25);
-  const auto t_end = t_begin + std::chrono::duration<double>(seconds * 1.25);
-  while (true) {
-    const bool warm = now() < t_warm;
-    if (!warm && samples >= 3 && now() > t_end) break;
-    std::shuffle(order.begin(), order.end(), rng);
-    for (int id : order) {
-      CK(cudaDeviceSynchronize());
-      const auto t0 = now();
-      fns[id].f();
-      const auto t_ret = now();   // the call has returned (launch enqueued), the GPU may still be running
-      CK(cudaDeviceSynchronize());
-      const double ms = std::chrono::duration<double, std::milli>(now() - t0).count();
-      if (!warm) { sum_tf[id] += flops / ms * 1e-9; sum_ms[id] += ms; sum_call_ms[id] += std::chrono::duration<double, std::milli>(t_ret - t0).count(); }
+  static uint32_t draw = 1;
+  auto new_operands = [&] {   // run_all_perf_funcs_once, benchmarking_utils.py:35-58
+    fill_randn<<<g1(ea), 256>>>(w.A0, ea, 0x1234567u + 7919u * draw);
+    fill_randn<<<g1(eb), 256>>>(w.B0, eb, 0x89abcdeu + 104729u * draw);
+    ++draw;
+    for (int f = 0; f < 2; ++f) {
+      CK(cudaMemcpyAsync(w.A[f], w.A0, ea * 2, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpyAsync(w.Brow[f], w.B0, eb * 2, cudaMemcpyDeviceToDevice));
+      transpose_rc<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8)>>>(w.Brow[f], w.Bt[f], K, N);
+      fill_randn<<<g1(ec), 256>>>(w.C[f], ec, 0x5555u + 31u * draw + f);
     }
-    if (!warm) ++samples;
+    CK(cudaDeviceSynchronize());
+  };
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto timed = [&](int which, const std::function<int()>& f, double* ms, double* call_ms) {   // run_benchmark, :12-33
+    CK(cudaMemsetAsync(w.C[which], 0, ec * 2));
+    CK(cudaDeviceSynchronize());
+    const auto t0 = now();
+    const int st = f();
+    const auto t_ret = now();
+    CK(cudaDeviceSynchronize());
+    *ms = std::chrono::duration<double, std::milli>(now() - t0).count();
+    *call_ms = std::chrono::duration<double, std::milli>(t_ret - t0).count();
+    return st;
+  };
+  std::vector<int> order(base.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
+  std::mt19937 rng(12345u + uint32_t(M) * 31u + uint32_t(N) * 17u + uint32_t(K));
+  std::shuffle(order.begin(), order.end(), rng);
+  std::vector<double> base_tf(base.size(), 0.0), ours_tf(base.size(), 0.0), base_ms(base.size(), 0.0), ours_ms(base.size(), 0.0);
+  std::vector<int> iters(base.size(), 0);
+  double ours_call_ms = 0.0, base_call_ms = 0.0; int calls = 0;
+  for (int bi : order) {
+    const double bench_s = base[bi].primary ? seconds : 0.4 * seconds, warm_s = 0.25 * bench_s;
+    new_operands();
+    if (base[bi].f() || ours()) { printf("WALLFAIL,%d,%d,%d,%d,first call failed: %s\n", acc, M, N, K, base[bi].name); return 1; }
+    CK(cudaDeviceSynchronize());
+    const auto t_begin = now();
+    int warm_iters = 0;
+    while (warm_iters < 1 || std::chrono::duration<double>(now() - t_begin).count() < warm_s) {
+      new_operands();
+      double ms, cm;
+      timed(0, base[bi].f, &ms, &cm); timed(1, ours, &ms, &cm);
+      ++warm_iters;
+    }
+    const auto t_bench = now();
+    while (iters[bi] < 3 || std::chrono::duration<double>(now() - t_bench).count() < bench_s) {
+      new_operands();
+      const bool ours_first = rng() & 1u;   // random.shuffle of the two-element list
+      double ms_b = 0, ms_o = 0, cm_b = 0, cm_o = 0;
+      if (ours_first) { timed(1, ours, &ms_o, &cm_o); timed(0, base[bi].f, &ms_b, &cm_b); }
+      else { timed(0, base[bi].f, &ms_b, &cm_b); timed(1, ours, &ms_o, &cm_o); }
+      base_tf[bi] += flops / ms_b * 1e-9; ours_tf[bi] += flops / ms_o * 1e-9;
+      base_ms[bi] += ms_b; ours_ms[bi] += ms_o;
+      ours_call_ms += cm_o; base_call_ms += cm_b; ++calls;
+      ++iters[bi];
+    }
   }
   int cfg, gm, sp; b200_hgemm_select(acc, M, N, K, &cfg, &gm, &sp);
-  printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d,tune_rounds=%d+%d", acc, M, N, K, samples, cfg, gm, sp, cand[1], cand[0], tune_warm, tune_bench);
-  for (size_t i = 0; i < fns.size(); ++i) printf(",%s=%.6g", fns[i].name, sum_tf[i] / samples);
-  const double hard_auto = std::max(sum_tf[5], sum_tf[6]);
-  printf(",speedup_vs_lt_auto_max=%.3f,ours_us=%.2f,lt_auto_tn_us=%.2f,ours_call_us=%.2f,cublas_call_us=%.2f,lt_auto_call_us=%.2f\n", sum_tf[0] / hard_auto, sum_ms[0] / samples * 1e3, sum_ms[5] / samples * 1e3,
-         sum_call_ms[0] / samples * 1e3, sum_call_ms[1] / samples * 1e3, sum_call_ms[5] / samples * 1e3);
+  double ours_mean = 0.0, ours_ms_mean = 0.0; int samples = 0;
+  for (size_t i = 0; i < base.size(); ++i) { ours_mean += ours_tf[i] / iters[i]; ours_ms_mean += ours_ms[i] / iters[i]; samples += iters[i]; }
+  ours_mean /= base.size(); ours_ms_mean /= base.size();
+  printf("WALL,%d,%d,%d,%d,samples=%d,cfg=%d,gm=%d,splits=%d,lt_candidates=%d/%d,tune_rounds=%d+%d,protocol=pairs,ours=%.6g", acc, M, N, K,
+         samples, cfg, gm, sp, cand[1], cand[0], tune_warm, tune_bench, ours_mean);
+  double sp_auto[2] = {0, 0};
+  for (size_t i = 0; i < base.size(); ++i) {
+    const double b = base_tf[i] / iters[i], o = ours_tf[i] / iters[i];
+    printf(",%s=%.6g,%s_speedup=%.4f,%s_n=%d", base[i].name, b, base[i].name, o / b, base[i].name, iters[i]);
+    if (i == 4) sp_auto[0] = o / b;
+    if (i == 5) sp_auto[1] = o / b;
+  }
+  printf(",speedup_vs_lt_auto_max=%.4f,ours_us=%.2f,lt_auto_tn_us=%.2f,ours_call_us=%.2f,baseline_call_us=%.2f\n", std::min(sp_auto[0], sp_auto[1]),
+         ours_ms_mean * 1e3, base_ms[4] / iters[4] * 1e3, ours_call_ms / calls * 1e3, base_call_ms / calls * 1e3);
   fflush(stdout);
   return 0;
 }
 
-// wall: the harness metric in C++ — host wall clock around ONE call bracketed by device synchronisation
-// (reference benchmarking_utils.py:23-31), mean of per-sample TFLOP/s, our dispatcher against the six library
-// baselines (cuBLASLt auto-tuning runs the reference's 50 + 100 round search first unless rounds are given).
 static int do_wall(int acc, int M, int N, int K, double seconds, int tune_warm, int tune_bench) {
-  Problem p; alloc_random(p, M, N, K);
-  __half* Brow;   // row-major B [K,N] for the NN baselines
-  CK(cudaMalloc(&Brow, size_t(K) * N * 2));
-  fill_normalish<<<g1(size_t(K) * N), 256>>>(Brow, size_t(K) * N, 0x5555u);
-  CK(cudaDeviceSynchronize());
+  WallBuffers w;
+  w.alloc(std::max(std::max(size_t(M) * K, size_t(K) * N), size_t(M) * N));
   if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
-  int rc = wall_one(acc, p, Brow, seconds, tune_warm, tune_bench);
-  cudaFree(Brow);
-  p.release();
+  int rc = wall_one(acc, M, N, K, w, seconds, tune_warm, tune_bench);
+  w.release();
   return rc;
 }
 
 // wallgrid: `wall` over this process's share of the 1001-shape grid (shapes sorted by cost, dealt round-robin
 // to `nparts` processes — one per GPU), all in one process so that CUDA/cuBLAS start-up is paid once.
+// B200_WALLGRID_SHAPES=<file of "M N K" lines> replaces the grid (stratified samples, reruns of single shapes).
 static int do_wallgrid(int acc, int part, int nparts, double seconds, int tune_warm, int tune_bench, int limit) {
   const int G[10] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 12288, 16384};
   std::vector<std::array<int, 3>> shapes;
-  for (int a : G) for (int b : G) for (int c : G) shapes.push_back({a, b, c});
-  shapes.push_back({2048, 11008, 4096});
+  if (const char* path = getenv("B200_WALLGRID_SHAPES")) {
+    FILE* f = fopen(path, "r");
+    if (!f) { printf("cannot open %s\n", path); return 1; }
+    int a, b, c;
+    while (fscanf(f, "%d %d %d", &a, &b, &c) == 3) shapes.push_back({a, b, c});
+    fclose(f);
+  } else {
+    for (int a : G) for (int b : G) for (int c : G) shapes.push_back({a, b, c});
+    shapes.push_back({2048, 11008, 4096});
+  }
   auto cost = [](const std::array<int, 3>& s) { return double(s[0]) * s[1] * s[2] + 3e9 * (double(s[0]) * s[1] + double(s[1]) * s[2] + double(s[0]) * s[2]) / 1e6; };
   std::stable_sort(shapes.begin(), shapes.end(), [&](const auto& x, const auto& y) { return cost(x) > cost(y); });
-  const size_t maxe = size_t(16384) * 16384;
-  Problem p;
-  __half* Brow;
-  CK(cudaMalloc(&p.A, maxe * 2)); CK(cudaMalloc(&p.Bt, maxe * 2));
-  CK(cudaMalloc(&p.Cbuf, maxe * 2)); CK(cudaMalloc(&p.Cref, maxe * 2)); CK(cudaMalloc(&Brow, maxe * 2));
-  p.C = p.Cbuf;
-  fill_normalish<<<g1(maxe), 256>>>(p.A, maxe, 0x1234567u);
-  fill_normalish<<<g1(maxe), 256>>>(p.Bt, maxe, 0x89abcdeu);
-  fill_normalish<<<g1(maxe), 256>>>(Brow, maxe, 0x5555u);
-  CK(cudaDeviceSynchronize());
+  size_t maxe = 0;
+  for (const auto& sh : shapes)
+    maxe = std::max(maxe, std::max(std::max(size_t(sh[0]) * sh[2], size_t(sh[2]) * sh[1]), size_t(sh[0]) * sh[1]));
+  WallBuffers w;
+  w.alloc(maxe);
   if (b200_bl_init(acc)) { printf("baseline init failed\n"); return 1; }
   int done = 0, failed = 0;
+  const auto t0 = std::chrono::steady_clock::now();
   for (size_t si = 0; si < shapes.size(); ++si) {
     if (int(si % nparts) != part) continue;
     if (limit > 0 && done >= limit) break;
-    p.M = shapes[si][0]; p.N = shapes[si][1]; p.K = shapes[si][2];
-    failed += wall_one(acc, p, Brow, seconds, tune_warm, tune_bench);
+    failed += wall_one(acc, shapes[si][0], shapes[si][1], shapes[si][2], w, seconds, tune_warm, tune_bench);
     ++done;
   }
-  printf("WALLGRID done=%d failed=%d\n", done, failed);
+  printf("WALLGRID done=%d failed=%d seconds=%.1f\n", done, failed, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  w.release();
   return failed ? 1 : 0;
 }
 

@@ -64,7 +64,8 @@ inline EncodeTiledFn encode_fn() {
 
 // Row-major fp16 matrix [rows, cols] (cols contiguous) -> 2-D tiled map, 128B swizzle,
 // box = {box_cols (64 or 32) columns, box_rows}. Out-of-bounds elements read as zero / are not written.
-inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols = kBlockK) {
+inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int box_cols = kBlockK,
+                     bool bf16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return kNoDriver;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
@@ -80,7 +81,7 @@ inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int 
     return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
          : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   }();
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? kOk : kEncodeFailed;
 }
@@ -88,9 +89,9 @@ inline int encode_2d(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 // Small direct-mapped cache of encoded maps: benchmark loops re-present the same few pointers
 // (the caching allocator recycles them), and an encode costs about a microsecond of host time.
 struct MapKey {
-  const void* ptr; int rows, cols, box_rows, box_cols;
+  const void* ptr; int rows, cols, box_rows, box_cols; bool bf16;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols && bf16 == o.bf16;
   }
 };
 struct MapCache {
@@ -100,14 +101,14 @@ struct MapCache {
   bool valid[kSlots];
   MapCache() { std::memset(valid, 0, sizeof(valid)); }
   // Copies the map out: two operands of one call may share a slot, so a pointer into the cache would alias.
-  int get(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out, int box_cols = kBlockK) {
-    MapKey k{ptr, rows, cols, box_rows, box_cols};
+  int get(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out, int box_cols = kBlockK, bool bf16 = false) {
+    MapKey k{ptr, rows, cols, box_rows, box_cols, bf16};
     uint64_t h = (reinterpret_cast<uint64_t>(ptr) >> 8) * 0x9E3779B97F4A7C15ull;
     h ^= uint64_t(uint32_t(rows)) * 0xC2B2AE3D27D4EB4Full + uint64_t(uint32_t(cols)) * 0x165667B19E3779F9ull +
          uint64_t(box_rows) * 131u + uint64_t(box_cols);
     int slot = int((h >> 32) % kSlots);
     if (!(valid[slot] && keys[slot] == k)) {
-      int st = encode_2d(&maps[slot], ptr, rows, cols, box_rows, box_cols);
+      int st = encode_2d(&maps[slot], ptr, rows, cols, box_rows, box_cols, bf16);
       if (st != kOk) { valid[slot] = false; return st; }
       keys[slot] = k;
       valid[slot] = true;
@@ -306,6 +307,12 @@ inline bool cooperative_enabled() {
   return on;
 }
 
+// B200_HGEMM_NO_PDL=1 launches without programmatic stream serialisation (developer A/B).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200_HGEMM_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 // One (configuration, K-mode) instance of the kernel: opt into its dynamic shared memory once, then launch.
 // Function attributes are per device AND per copy of the kernel: when two shared objects instantiate this template
 // (libb200_hgemm.so and a JIT-built hgemm_lib.so in one process), a function-local static may be merged across
@@ -338,7 +345,7 @@ int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
   cfg.blockDim = dim3(Cfg::NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = a.stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   unsigned na = 0;
   if (cluster > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -355,6 +362,14 @@ int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
   if ((KMODE == kWorkspaceSplitK || KMODE == kStreamK) && cooperative_enabled()) {
     attr[na].id = cudaLaunchAttributeCooperative;
     attr[na].val.cooperative = 1;
+    ++na;
+  }
+  else if (pdl_enabled()) {
+    // programmatic dependent launch: this kernel's prologue may overlap the tail of the stream's previous kernel; the
+    // kernel itself waits (griddepcontrol.wait) before its first global-memory access. Back-to-back GEMMs lose the
+    // 2-3 us of launch + set-up between them; a caller that synchronises after every call sees no difference.
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
   cfg.attrs = attr;
@@ -378,9 +393,9 @@ int launch(const void* A, const void* Bt, void* C, int M, int N, int K, cudaStre
 
   LaunchArgs a{};
   MapCache& cache = map_cache();
-  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &a.ma)) != kOk) return st;
-  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &a.mb)) != kOk) return st;
-  if ((st = cache.get(C, M, N, 32, &a.mc, Cfg::EPI_N)) != kOk) return st;
+  if ((st = cache.get(A, M, K, Cfg::A_BOX_ROWS, &a.ma, kBlockK, Cfg::BF16)) != kOk) return st;
+  if ((st = cache.get(Bt, N, K, Cfg::B_BOX_ROWS, &a.mb, kBlockK, Cfg::BF16)) != kOk) return st;
+  if ((st = cache.get(C, M, N, 32, &a.mc, Cfg::EPI_N, Cfg::BF16)) != kOk) return st;
 
   constexpr bool kCanSplit = Cfg::SPLIT_K && (MODES & ((1u << kWorkspaceSplitK) | (1u << kClusterSplitK)));
   constexpr bool kCanStream = Cfg::STREAM_K && (MODES & (1u << kStreamK));

@@ -91,12 +91,16 @@ __device__ __forceinline__ void trace_value(int slot, unsigned long long v) {
 #define B200_TRACE_ONLY(...)
 #endif
 
-template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1, int M_REP_ = 1>
+template <int BN_, int STAGES_, int CTA_GROUP_, bool ACC_F32_, int CLUSTER_M_ = 1, int CLUSTER_N_ = 1, int M_REP_ = 1, bool BF16_ = false>
 struct Config {
   static constexpr int BN = BN_;               // tile N (= UMMA N)
   static constexpr int STAGES = STAGES_;
   static constexpr int CTA_GROUP = CTA_GROUP_; // 1: 128xBN per CTA; 2: 256xBN per CTA pair
   static constexpr bool ACC_F32 = ACC_F32_;
+  // bf16 operands and bf16 output instead of fp16 (README.md:73 "denser configurations" territory): same pipeline, two
+  // instruction-descriptor fields and the epilogue's convert differ. tcgen05 kind::f16 accumulates bf16 products in fp32 only.
+  static constexpr bool BF16 = BF16_;
+  static_assert(!BF16_ || ACC_F32_, "bf16 operands accumulate in fp32");
   // Multicast cluster: CLUSTER_M x CLUSTER_N groups (single CTAs or CTA pairs) work on a block of adjacent tiles;
   // the groups of a cluster row share their A tile, those of a cluster column their B tile. Each CTA loads a
   // 1/CLUSTER_N slice of its A rows and a 1/CLUSTER_M slice of its B rows and TMA-multicasts it to the CTAs
@@ -157,8 +161,9 @@ struct Config {
 // 32-bit tcgen05 instruction descriptor for kind::f16, fp16 A/B, both K-major.
 // [4,6) D fmt (0=f16,1=f32) | [7,10) A fmt (0=f16) | [10,13) B fmt | [15] A major | [16] B major
 // | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool acc_f32) {
-  return (acc_f32 ? 1u : 0u) << 4 | (uint32_t(umma_n >> 3) << 17) | (uint32_t(umma_m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool acc_f32, bool bf16 = false) {
+  return (acc_f32 ? 1u : 0u) << 4 | (bf16 ? 1u : 0u) << 7 | (bf16 ? 1u : 0u) << 10 | (uint32_t(umma_n >> 3) << 17) |
+         (uint32_t(umma_m >> 4) << 24);
 }
 
 // 64-bit shared-memory matrix descriptor: K-major tile, 128B swizzle, rows 128 B apart,
@@ -256,8 +261,8 @@ __device__ __forceinline__ void splitk_epilogue(uint32_t taddr0, int q, int lane
         acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
       }
       uint2 out;
-      out.x = pack_f16x2_rn(acc.x, acc.y);
-      out.y = pack_f16x2_rn(acc.z, acc.w);
+      out.x = pack_out_x2_rn<Cfg::BF16>(acc.x, acc.y);
+      out.y = pack_out_x2_rn<Cfg::BF16>(acc.z, acc.w);
       *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
     }
   }
@@ -335,8 +340,8 @@ __device__ __forceinline__ void cluster_splitk_reduce(int e, int split, int spli
       }
     }
     uint2 out;
-    out.x = pack_f16x2_rn(acc.x, acc.y);
-    out.y = pack_f16x2_rn(acc.z, acc.w);
+    out.x = pack_out_x2_rn<Cfg::BF16>(acc.x, acc.y);
+    out.y = pack_out_x2_rn<Cfg::BF16>(acc.z, acc.w);
     *reinterpret_cast<uint2*>(C + size_t(gm) * N + gn) = out;
   }
 }
@@ -502,7 +507,7 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
         if (last) release_tmem();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          packed[16 * h + i] = pack_f16x2_rn(f[2 * i] + __uint_as_float(v[2 * i]), f[2 * i + 1] + __uint_as_float(v[2 * i + 1]));
+          packed[16 * h + i] = pack_out_x2_rn<Cfg::BF16>(f[2 * i] + __uint_as_float(v[2 * i]), f[2 * i + 1] + __uint_as_float(v[2 * i + 1]));
       } else {
         uint32_t r[SK::REGS];
         streamk_load_chunk<Cfg>(taddr0 + j * Cfg::EPI_N, r);
@@ -510,7 +515,7 @@ __device__ __forceinline__ void streamk_own(const EpilogueWarp& w, uint32_t tadd
 #pragma unroll
         for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
           const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
-          packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+          packed[i] = pack_out_x2_rn<Cfg::BF16>(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
         }
       }
     }
@@ -603,7 +608,7 @@ __device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t
         if (last && h == 1) release_tmem();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          packed[16 * h + i] = pack_f16x2_rn(f[32 * h + 2 * i] + __uint_as_float(v[2 * i]),
+          packed[16 * h + i] = pack_out_x2_rn<Cfg::BF16>(f[32 * h + 2 * i] + __uint_as_float(v[2 * i]),
                                              f[32 * h + 2 * i + 1] + __uint_as_float(v[2 * i + 1]));
       }
     } else {
@@ -613,7 +618,7 @@ __device__ __forceinline__ void streamk_own_bulk(const EpilogueWarp& w, uint32_t
 #pragma unroll
       for (int i = 0; i < Cfg::EPI_N / 2; ++i) {
         const __half2 hh = *reinterpret_cast<const __half2*>(&r[i]);
-        packed[i] = pack_f16x2_rn(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
+        packed[i] = pack_out_x2_rn<Cfg::BF16>(f[2 * i] + __low2float(hh), f[2 * i + 1] + __high2float(hh));
       }
     }
     epilogue_store_chunk<Cfg>(packed, w.epi_buf, w.row_off, w.sw, w.lane, tmap_c, n0 + j * Cfg::EPI_N, m0, M, N);
@@ -762,6 +767,15 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
 #endif
   B200_TRACE_ONLY(if (threadIdx.x == 64) B200_TRACE(1);)
 
+  // Programmatic dependent launch (the host sets cudaLaunchAttributeProgrammaticStreamSerialization): this grid may have
+  // been started while the previous kernel of the stream was still running, so that everything above — barrier
+  // initialisation, TMEM allocation, descriptor prefetch, the set-up barrier — overlaps that kernel's tail instead of
+  // following it. Nothing above touches global memory; everything below may, so every thread first waits until the
+  // prerequisite grids have completed and their writes are visible (a no-op for an ordinary launch). The next kernel
+  // of the stream may in turn begin ITS prologue as soon as SMs free up.
+  ptx::grid_dependency_launch_dependents();
+  ptx::grid_dependency_wait();
+
   [[maybe_unused]] int ck_m_base = 0, ck_n0 = 0, ck_split = 0;   // cluster split-K: where this CTA's unit lives (set by the epilogue warps)
 
   // ------------------------------------------------------------------ roles
@@ -823,7 +837,7 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
     // ===== MMA issuer: the whole warp of the leader CTA walks the schedule (so loop state stays in uniform
     // registers and the waits are warp-wide), one elected lane issues tcgen05.mma / tcgen05.commit =====
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc(kBlockM * CG, BN, Cfg::ACC_F32);   // one MMA covers 128 rows per CTA of the group
+      constexpr uint32_t idesc = make_idesc(kBlockM * CG, BN, Cfg::ACC_F32, Cfg::BF16);   // one MMA covers 128 rows per CTA of the group
       const uint64_t desc_a0 = make_smem_desc(smem_a);
       const uint64_t desc_b0 = make_smem_desc(smem_b);
       // who must learn that a stage has been consumed: the pair (pair mode), or every CTA that multicasts
@@ -973,13 +987,13 @@ hgemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,   // A  [M,K]  box {
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              packed[16 + i] = pack_f16x2_rn(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+              packed[16 + i] = pack_out_x2_rn<Cfg::BF16>(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
           } else {
             tmem_ld_wait();
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            packed[i] = pack_f16x2_rn(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+            packed[i] = pack_out_x2_rn<Cfg::BF16>(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
         } else {
           if constexpr (EN == 64) tmem_ld_32x32b_x32_pack16(taddr0 + j * EN, packed);
           else tmem_ld_32x32b_x16_pack16(taddr0 + j * EN, packed);

@@ -4,6 +4,7 @@
 // and the SASS that nvcc 12.9 emits (UTCHMMA / UTMALDG / UTMASTG / LDTM / UTCBAR).
 #pragma once
 #include <cstdint>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #ifndef B200_HGEMM_WATCHDOG
@@ -334,6 +335,14 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void grid_dependency_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -363,6 +372,16 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);   // cvt.rn.f16x2.f32: one rounding per element
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // cvt.rn.bf16x2.f32
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// the output element type follows the operands': fp16 in -> fp16 out, bf16 in -> bf16 out
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack_out_x2_rn(float lo, float hi) {
+  if constexpr (kBf16) return pack_bf16x2_rn(lo, hi);
+  else return pack_f16x2_rn(lo, hi);
 }
 
 

@@ -63,8 +63,14 @@ def speedup_row(mnk: str, tf: dict) -> dict:
     ours = tf["ours"]
     row = {"mnk": mnk, "torch.matmul": (ours / tf["matmul"]) if tf.get("matmul") else ""}
     for fam, key in (("cuBLAS", "cublas"), ("cuBLASLt-heuristic", "lt_heur"), ("cuBLASLt-auto-tuning", "lt_auto")):
-        tn, nn = ours / tf[f"{key}_tn"], ours / tf[f"{key}_nn"]
-        row[f"{fam}-tn"], row[f"{fam}-nn"], row[f"{fam}-max"] = tn, nn, min(tn, nn)
+        if tf.get(f"{key}_tn") and tf.get(f"{key}_nn"):
+            # a pair-protocol record carries the speed-up measured inside each (baseline, ours) pair — the harness's own
+            # number; older records only have absolute rates
+            tn = tf.get(f"{key}_tn_speedup") or ours / tf[f"{key}_tn"]
+            nn = tf.get(f"{key}_nn_speedup") or ours / tf[f"{key}_nn"]
+            row[f"{fam}-tn"], row[f"{fam}-nn"], row[f"{fam}-max"] = tn, nn, min(tn, nn)
+        else:                                   # a baseline the run did not time (eval_one_file.sh --perf_funcs)
+            row[f"{fam}-tn"] = row[f"{fam}-nn"] = row[f"{fam}-max"] = ""
     return row
 
 
@@ -105,36 +111,55 @@ HARNESS_KEYS = {"torch.matmul": "matmul", "cuBLAS-tn": "cublas_tn", "cuBLAS-nn":
 def record_from_harness_summary(summary: dict) -> dict:
     """{base_dir}/summary.json of one eval_one_file.sh run (written by summarize_result.py) -> a sweep record.
     Every baseline process timed the kernel again; `ours` is their mean, each baseline keeps its own pairing through
-    the stored speed-ups, so the "-max" columns are exactly the harness's."""
+    the stored speed-ups, so the "-max" columns are exactly the harness's. Baselines that were not run (eval_one_file.sh
+    --perf_funcs) are simply absent; the two cuBLASLt-auto-tuning layouts are required."""
     rec, ours = {}, []
     for name, key in HARNESS_KEYS.items():
+        if name not in summary:
+            continue
         row = summary[name]
         ours.append(row["CUDA-L2 TFLOPS"])
         rec[key + "_speedup"] = row["Speedup"]
     rec["ours"] = sum(ours) / len(ours)
     for key in HARNESS_KEYS.values():          # baselines re-expressed against the common `ours`
-        rec[key] = rec["ours"] / rec[key + "_speedup"]
+        if key + "_speedup" in rec:
+            rec[key] = rec["ours"] / rec[key + "_speedup"]
     rec["speedup_vs_lt_auto_max"] = min(rec["lt_auto_tn_speedup"], rec["lt_auto_nn_speedup"])
     return rec
 
 
+AUTO_TUNING_PAIR = "hgemm_cublaslt_auto_tuning_tn,hgemm_cublaslt_auto_tuning_nn"
+
+
 def run_harness_engine(shape, acc_precise: str, warmup_s: float, bench_s: float, gpu: int | None, base_dir: Path,
-                       mode: str = "offline", target_qps: float | None = None) -> dict:
-    """The reference-style flow for one shape: eval_one_file.sh (JIT build, 0/1 check, 7 baseline processes, summary)."""
+                       mode: str = "offline", target_qps: float | None = None, perf_funcs: str | None = None,
+                       shared_build_dir: bool = True) -> dict:
+    """The reference-style flow for one shape: eval_one_file.sh (JIT build, 0/1 check, one fresh process per baseline,
+    summary). ``perf_funcs`` restricts the baselines (None = all seven). With ``shared_build_dir`` every shape of a
+    worker builds in the same directory, so ninja recompiles only kernels/.../<mnk>.cu (the three library sources and
+    the binding are shape-independent); each shape's summary is copied to ``<base_dir>/summaries/<mnk>.json``."""
     m, n, k = shape
+    mnk = f"{m}_{n}_{k}"
     env = dict(os.environ)
     if gpu is not None:
         env["CUDA_VISIBLE_DEVICES"] = str(gpu)      # the worker then addresses its GPU as device 0
-    out = Path(base_dir) / f"{m}_{n}_{k}"
-    cmd = [str(REPO / "eval_one_file.sh"), "--mnk", f"{m}_{n}_{k}", "--acc_precise", acc_precise, "--device_type", "b200",
+    base_dir = Path(base_dir)
+    out = base_dir / (f"build_{acc_precise}_{gpu if gpu is not None else 0}" if shared_build_dir else mnk)
+    cmd = [str(REPO / "eval_one_file.sh"), "--mnk", mnk, "--acc_precise", acc_precise, "--device_type", "b200",
            "--warmup_seconds", str(warmup_s), "--benchmark_seconds", str(bench_s), "--base_dir", str(out),
            "--gpu_device_id", "0", "--mode", mode]
     if mode == "server":
         cmd += ["--target_qps", str(target_qps or 100)]
+    if perf_funcs:
+        cmd += ["--perf_funcs", perf_funcs]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3600)
     if r.returncode != 0:
         raise RuntimeError(f"eval_one_file.sh failed for {shape}: rc={r.returncode}\n{r.stdout[-1500:]}\n{r.stderr[-1500:]}")
-    return record_from_harness_summary(json.loads((out / "summary.json").read_text()))
+    summary = json.loads((out / "summary.json").read_text())
+    keep = base_dir / "summaries"
+    keep.mkdir(parents=True, exist_ok=True)
+    (keep / f"{mnk}_{acc_precise}_{mode}.json").write_text(json.dumps(summary, indent=1))
+    return record_from_harness_summary(summary)
 
 
 def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tune_rounds: tuple[int, int],
@@ -251,13 +276,13 @@ def write_reports(records: list[dict], out_csv: Path, peak_tflops: float, peak_g
     by_class = {k: {"shapes": len(v), "won": sum(x >= 1.0 for x in v), "mean_speedup": (sum(v) / len(v)) if v else None}
                 for k, v in classes.items()}
     baseline_rows = {r["mnk"]: {"ours_tflops": r["ours"], "speedup_vs_lt_auto_max": r["speedup_vs_lt_auto_max"],
-                                "speedup_vs_cublas_max": r["ours"] / max(r["cublas_tn"], r["cublas_nn"]),
+                                "speedup_vs_cublas_max": (r["ours"] / max(r["cublas_tn"], r["cublas_nn"])) if r.get("cublas_tn") and r.get("cublas_nn") else None,
                                 "cfg": r.get("cfg"), "gm": r.get("gm"), "splits": r.get("splits")}
                      for r in ok if r["mnk"] in ("64_4096_64", "4096_4096_4096", "8192_8192_8192", "2048_11008_4096")}
     return {"shapes": n, "failed": [r["mnk"] for r in records if not r.get("ok")], "by_class": by_class,
             "baseline_config_shapes": baseline_rows,
-            "won_vs_cublas_max": sum(r["ours"] >= max(r["cublas_tn"], r["cublas_nn"]) for r in ok),
-            "won_vs_lt_heuristic_max": sum(r["ours"] >= max(r["lt_heur_tn"], r["lt_heur_nn"]) for r in ok),
+            "won_vs_cublas_max": sum(r["ours"] >= max(r["cublas_tn"], r["cublas_nn"]) for r in ok if r.get("cublas_tn") and r.get("cublas_nn")),
+            "won_vs_lt_heuristic_max": sum(r["ours"] >= max(r["lt_heur_tn"], r["lt_heur_nn"]) for r in ok if r.get("lt_heur_tn") and r.get("lt_heur_nn")),
             "won_vs_lt_auto_max": wins, "win_fraction": wins / n if n else float("nan"), "mean_speedup_vs_lt_auto_max": mean,
             "aggregate_tflops": (sum(_flops(r["mnk"]) for r in ok) /
                                  sum(_flops(r["mnk"]) / (r["ours"] * 1e12) for r in ok) * 1e-12) if n else 0.0}

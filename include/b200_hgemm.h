@@ -38,6 +38,15 @@ int b200_hgemm_f32acc(const void* A, const void* B_rowmajor, const void* B_kmajo
 int b200_hgemm_f16acc(const void* A, const void* B_rowmajor, const void* B_kmajor, void* C,
                       int M, int N, int K, void* stream);
 
+/* bf16 variant (README.md:73 lists further data types as future work; no reference kernel exists for it): bf16 x bf16
+ * products, fp32 accumulation, one round-to-nearest-even conversion to bf16. Same layouts, same dispatcher (the fp32-
+ * accumulate table), same pipeline — the MMA instruction descriptor names bf16 operands and the epilogue converts with
+ * cvt.rn.bf16x2.f32. b200_bgemm_run_config is b200_hgemm_run_config for this data type. */
+int b200_bgemm_f32acc(const void* A, const void* B_rowmajor, const void* B_kmajor, void* C,
+                      int M, int N, int K, void* stream);
+int b200_bgemm_run_config(int config_id, const void* A, const void* B_kmajor, void* C,
+                          int M, int N, int K, int group_m, int max_ctas, int splits, void* stream);
+
 /* The reference fixes tile/stage/swizzle per (M,N,K) at compile time inside each
  * kernels/<dev>/<M>_<N>_<K>.cu (e.g. a100_F32F16F16F32/4096_4096_4096.cu:185-200,305-309). Here the
  * per-shape choice is a table lookup; these calls expose it for the tuner and the tests. */

@@ -162,6 +162,48 @@ void oracle_hgemm_f16acc(const uint16_t* A, const uint16_t* Bt, uint16_t* C, int
   free(b);
 }
 
+/* ---- bf16 variant (an extension of this repository: the reference ships no bf16 kernel, README.md:73 lists
+ * further data types as future work). Same contract as F32F16F16F32 with bfloat16 operands and output:
+ * exact bf16 x bf16 products (8 x 8 significant bits), fp32 accumulation, ONE round-to-nearest-even
+ * conversion to bf16 — what torch.matmul(a.float(), b.float()).bfloat16() computes, which is the expression
+ * tests/golden/make_golden.py uses to pin it (0/1 operands, K <= 256 so that every sum is a bf16 integer).
+ * PARITY UNPINNED by the reference (it defines no bf16 result); pinned against that torch expression. */
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+/* round-to-nearest-even on the upper 16 bits, NaN kept quiet — cvt.rn.bf16.f32 */
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+uint16_t oracle_f32_to_bf16(float f) { return f2bf(f); }
+float oracle_bf16_to_f32(uint16_t h) { return bf2f(h); }
+
+void oracle_bgemm_f32acc(const uint16_t* A, const uint16_t* Bt, uint16_t* C, int M, int N, int K) {
+  float* a = (float*)malloc((size_t)M * K * sizeof(float));
+  float* b = (float*)malloc((size_t)N * K * sizeof(float));
+  for (size_t i = 0; i < (size_t)M * K; ++i) a[i] = bf2f(A[i]);
+  for (size_t i = 0; i < (size_t)N * K; ++i) b[i] = bf2f(Bt[i]);
+#pragma omp parallel for schedule(static)
+  for (int m = 0; m < M; ++m) {
+    const float* am = a + (size_t)m * K;
+    for (int n = 0; n < N; ++n) {
+      const float* bn = b + (size_t)n * K;
+      float acc = 0.0f;
+      for (int k = 0; k < K; ++k) acc += am[k] * bn[k];   /* one fp32 accumulator, k ascending */
+      C[(size_t)m * N + n] = f2bf(acc);
+    }
+  }
+  free(a);
+  free(b);
+}
+
 /* ---- the reference's pass rule (zero_one_correctness_check.py:92,169-172): ---------------------
  * diff = |out - truth| in fp16 arithmetic (torch subtracts the two half tensors), entries with
  * |truth| > 2047 are ignored, result = max diff. Returns that max as float; *n_masked and *n_nonfinite

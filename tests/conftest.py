@@ -38,6 +38,23 @@ def load_randn_cases():
     return cases
 
 
+def load_bf16_cases():
+    """bf16 fixtures: operands and truth as uint16 bit patterns; kind 0 = 0/1, 1 = small integers (both exact), 2 = randn."""
+    z = np.load(GOLDEN / "bf16_cases.npz")
+    cases = []
+    i = 0
+    while f"meta{i}" in z:
+        m, n, k, kind, seed = (int(x) for x in z[f"meta{i}"])
+        cases.append(dict(m=m, n=n, k=k, kind=("01", "int", "randn")[kind], seed=seed, a=z[f"a{i}"], b=z[f"b{i}"], truth=z[f"truth{i}"]))
+        i += 1
+    return cases
+
+
+@pytest.fixture(scope="session")
+def bf16_cases():
+    return load_bf16_cases()
+
+
 @pytest.fixture(scope="session")
 def zero_one_cases():
     return load_zero_one_cases()

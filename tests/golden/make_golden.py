@@ -10,8 +10,15 @@ Everything is produced by the REFERENCE's own code or expressions, never by this
 * helpers.json         outputs of the reference's importable helpers tools/utils.py:
                        extract_bm_bk_bn on synthetic source snippets (ours), as_col_major on small tensors
 
+* bf16_cases.npz       the bf16 variant (this repository's extension; the reference has no bf16 kernel, so there is
+                       no reference code to run): bf16 operands as uint16 bit patterns and the truth
+                       ``torch.matmul(a.float(), b.float()).bfloat16()`` — the reference's truth expression with the output
+                       type swapped. Integer-valued cases are exact (|c| <= 256 fits bf16's 8 significant bits).
+
     python tests/golden/make_golden.py          # needs /root/reference; the GPU box only reads the outputs
+    python tests/golden/make_golden.py --bf16   # only (re)writes bf16_cases.npz (needs torch only)
 """
+import sys
 import importlib.util
 import json
 from pathlib import Path
@@ -67,7 +74,43 @@ SNIPPETS = {
 }
 
 
+BF16_CASES = [
+    # (m, n, k, kind, seed)   kind: "01" 0/1 operands (sums <= k <= 256: exact in bf16), "int" integers in [-2, 2]
+    # with k small enough that |c| <= 256 always, "randn" N(0,1) rounded to bf16 (tolerance tests)
+    (64, 256, 64, "01", 21), (200, 328, 72, "01", 22), (128, 64, 256, "01", 23), (384, 264, 136, "01", 24),
+    (256, 512, 64, "int", 25), (1, 8, 8, "01", 26),
+    (64, 128, 64, "randn", 31), (200, 328, 72, "randn", 32), (128, 128, 1024, "randn", 33),
+]
+
+
+def bits(t):
+    return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def make_bf16():
+    out = {}
+    for i, (m, n, k, kind, seed) in enumerate(BF16_CASES):
+        gen = torch.Generator().manual_seed(seed)
+        if kind == "01":
+            a = torch.randint(0, 2, (m, k), generator=gen).bfloat16()
+            b = torch.randint(0, 2, (k, n), generator=gen).bfloat16()
+        elif kind == "int":
+            a = (torch.randint(0, 5, (m, k), generator=gen) - 2).bfloat16()
+            b = (torch.randint(0, 5, (k, n), generator=gen) - 2).bfloat16()
+        else:
+            a = torch.randn((m, k), generator=gen).bfloat16()
+            b = torch.randn((k, n), generator=gen).bfloat16()
+        truth = torch.matmul(a.float(), b.float()).bfloat16()     # the reference's truth expression, bf16 output
+        out[f"a{i}"], out[f"b{i}"], out[f"truth{i}"] = bits(a), bits(b), bits(truth)
+        out[f"meta{i}"] = np.array([m, n, k, {"01": 0, "int": 1, "randn": 2}[kind], seed])
+    np.savez_compressed(HERE / "bf16_cases.npz", **out)
+    print("bf16 fixtures written")
+
+
 def main():
+    if "--bf16" in sys.argv:
+        make_bf16()
+        return
     utils = ref_utils()
     zo = {}
     for i, (m, n, k, levels, seed) in enumerate(ZERO_ONE_CASES):
@@ -98,6 +141,7 @@ def main():
         helpers["as_col_major"].append({"rows": rows, "cols": cols, "flat_out": y.flatten().tolist(),
                                         "shape_out": list(y.shape), "contiguous": bool(y.is_contiguous())})
     (HERE / "helpers.json").write_text(json.dumps(helpers, indent=1))
+    make_bf16()
     print("golden fixtures written to", HERE)
 
 

@@ -64,3 +64,29 @@ def test_offline_benchmark_cli_writes_result(base_dir):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     rec = json.loads((base_dir / "fp32" / "benchmark_result_hgemm_cublas_tn.json").read_text())["records"]
     assert rec["cuda_l2_b200_fp32"] > 0 and rec["hgemm_cublas_tn"] > 0 and rec["samples"] > 5
+
+
+def test_server_benchmark_cli_writes_result(base_dir):
+    """benchmarking_server.py (reference benchmarking_server.py:144-145: exponential inter-arrival sleeps at --target_qps)
+    end to end on one shape, reusing the extension built above."""
+    cmd = [sys.executable, str(REPO / "benchmarking_server.py"), "--mnk", "256_512_1024", "--acc_precise", "fp32",
+           "--device_type", "b200", "--warmup_seconds", "0.2", "--benchmark_seconds", "0.6", "--base_dir",
+           str(base_dir / "fp32"), "--gpu_device_id", "0", "--perf_func", "hgemm_cublaslt_auto_tuning_tn", "--target_qps", "400"]
+    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    rec = json.loads((base_dir / "fp32" / "benchmark_result_hgemm_cublaslt_auto_tuning_tn.json").read_text())["records"]
+    assert rec["cuda_l2_b200_fp32"] > 0 and rec["hgemm_cublaslt_auto_tuning_tn"] > 0
+    # at 400 requests/s for 0.6 s the loop cannot have collected many more than ~240 samples: the sleeps are real
+    assert 20 <= rec["samples"] <= 600
+
+
+def test_farm_harness_engine_runs_eval_one_file_for_a_shape(tmp_path):
+    """farm_sweep.py --engine harness = the reference-style eval_one_file.sh per shape (0/1 check, one process per
+    baseline, summary). Restricted to the cuBLASLt-auto-tuning pair, which is what the sweep's target needs."""
+    from cuda_l2_b200 import farm
+    rec = farm.run_harness_engine((256, 512, 1024), "fp32", 0.2, 0.6, None, tmp_path, perf_funcs=farm.AUTO_TUNING_PAIR)
+    assert rec["ours"] > 0 and rec["lt_auto_tn"] > 0 and rec["lt_auto_nn"] > 0
+    assert rec["speedup_vs_lt_auto_max"] == min(rec["lt_auto_tn_speedup"], rec["lt_auto_nn_speedup"])
+    assert (tmp_path / "summaries" / "256_512_1024_fp32_offline.json").exists()
+    row = farm.speedup_row("256_512_1024", rec)
+    assert row["cuBLASLt-auto-tuning-max"] == pytest.approx(rec["speedup_vs_lt_auto_max"]) and row["cuBLAS-max"] == ""

@@ -145,9 +145,12 @@ def test_stream_k_is_exact_deterministic_and_self_resetting(acc):
         plain_c = run(a, bt, acc, cfg=cfg)
         for _ in range(3):
             assert torch.equal(run(a, bt, acc, cfg=cfg, splits=capi.STREAMK_TAIL), first)
-        # a different summation grouping, not a different result: within a few fp16 ulps of the unsplit kernel
+        # a different summation grouping, not a different result. fp32 accumulation: within one fp16 ulp of the unsplit
+        # kernel at these magnitudes (|c| < 512: ulp 0.25). fp16 accumulation: both runs re-round a running sum of
+        # magnitude ~sqrt(K) = 90..400 to fp16 (ulp 0.06..0.25) some K/16 = 512 times, in different groupings — two
+        # random walks of half-ulps, whose difference measured 4.25 at worst on the B200; bound 8 = 32 ulps at 256..512
         err = (first.float() - plain_c.float()).abs()
-        assert float(err.max()) <= (0.25 if acc == "fp32" else 2.0), float(err.max())
+        assert float(err.max()) <= (0.25 if acc == "fp32" else 8.0), float(err.max())
 
 
 @pytest.mark.parametrize("acc", ACCS)

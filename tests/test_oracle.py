@@ -84,3 +84,32 @@ def test_max_diff_flags_errors():
     assert d == 1.0 and n_masked == 1 and n_bad == 0
     out[0, 0] = np.inf
     assert oracle.zero_one_max_diff(out, truth)[2] == 1
+
+
+def test_bf16_oracle_matches_the_torch_truth_expression(bf16_cases):
+    """bf16 variant (this repository's extension): the C restatement against fixtures generated with
+    torch.matmul(a.float(), b.float()).bfloat16() — bit-exact on the integer cases (every sum fits bf16's 8 bits),
+    within one bf16 ulp + summation noise on N(0,1) operands."""
+    for c in bf16_cases:
+        bt = np.ascontiguousarray(c["b"].T)
+        got = oracle.bgemm_f32acc(c["a"], bt)
+        if c["kind"] in ("01", "int"):
+            assert np.abs(oracle.bf16_bits_to_f32(c["truth"])).max() <= 256
+            assert np.array_equal(got, c["truth"]), (c["m"], c["n"], c["k"], c["kind"])
+        else:
+            g, t = oracle.bf16_bits_to_f32(got), oracle.bf16_bits_to_f32(c["truth"])
+            assert (np.abs(g - t) <= 2.0**-7 * np.abs(t) + 1e-2).all()
+
+
+def test_bf16_conversions_round_to_nearest_even():
+    lib = oracle.lib()
+    assert lib.oracle_f32_to_bf16(1.0) == 0x3F80 and lib.oracle_bf16_to_f32(0x3F80) == 1.0
+    assert lib.oracle_f32_to_bf16(1.00390625) == 0x3F80          # 1 + 2^-8: tie -> even (down)
+    assert lib.oracle_f32_to_bf16(1.01171875) == 0x3F82          # 1 + 3*2^-8: tie -> even (up)
+    assert lib.oracle_f32_to_bf16(257.0) == 0x4380               # 257 -> 256 (ties to even)
+    assert lib.oracle_f32_to_bf16(float("inf")) == 0x7F80
+    assert (lib.oracle_f32_to_bf16(float("nan")) & 0x7FC0) == 0x7FC0
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32) * 100
+    want = torch.from_numpy(x).bfloat16().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(oracle.f32_to_bf16_bits(x), want)
+    assert all(lib.oracle_f32_to_bf16(float(v)) == int(w) for v, w in zip(x[:256], want[:256]))
