@@ -433,18 +433,21 @@ def main():
                      "ms_per_step": sus_ms / sus_steps, "seconds": sus_ms * 1e-3}
 
     # ---- end-to-end leg: host buffers through the C ABI, copies inside the timed region
-    ha = torch.randn((m, k)).half().pin_memory()
-    hbt = torch.randn((n, k)).half().pin_memory()
-    hc = torch.empty((m, n), dtype=torch.half).pin_memory()
-    e2e_steps = args.e2e_steps or max(1, min(args.steps, 50))
-    for _ in range(3):
-        capi.hgemm_host(ha, hbt.view(k, n), hc, args.acc)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        capi.hgemm_host(ha, hbt.view(k, n), hc, args.acc)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # host buffers are allocated (and the calls made) from the CPUs local to this rank's GPU — what numactl would do
+    with capi.host_near_gpu(local_rank) as near:
+        ha = torch.randn((m, k)).half().pin_memory()
+        hbt = torch.randn((n, k)).half().pin_memory()
+        hc = torch.empty((m, n), dtype=torch.half).pin_memory()
+        e2e_steps = args.e2e_steps or max(1, min(args.steps, 50))
+        for _ in range(3):
+            capi.hgemm_host(ha, hbt.view(k, n), hc, args.acc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            capi.hgemm_host(ha, hbt.view(k, n), hc, args.acc)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        near_cpus = len(near.cpus) if near.cpus else None
     e2e_value = flops_step * e2e_steps * world / e2e_s * 1e-12
     clocks = sampler.stop() if rank == 0 else None
 
@@ -494,7 +497,8 @@ def main():
                                          "split_k": splits}},
             "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * (m * k + n * k),
-                    "d2h_bytes_per_step": 2 * m * n, "steps": e2e_steps, "api": "b200_hgemm_host (pinned host buffers)"},
+                    "d2h_bytes_per_step": 2 * m * n, "steps": e2e_steps, "api": "b200_hgemm_host (pinned host buffers, row-block pipelined H2D / GEMM / D2H)",
+                    "host_cpus_local_to_gpu": near_cpus},
             "gpu_launches": launches,
             "gpu_launches_all_legs": total_launches,
             "clocks": clocks,

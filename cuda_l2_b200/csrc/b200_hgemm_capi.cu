@@ -67,7 +67,7 @@ int run(int acc_bits, int id, const void* A, const void* Bt, void* C, int M, int
   return b200::host::kBadConfig;
 }
 
-constexpr int kHostBlocks = 4;   // row blocks of the pipelined host entry
+constexpr int kHostBlocks = 8;   // at most this many row blocks in the pipelined host entry
 struct HostCtx {
   std::mutex mu;
   void* dbuf = nullptr; size_t dcap = 0;
@@ -227,7 +227,10 @@ int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* h
   // Large problems are PCIe time: B goes first, then A in row blocks; the GEMM of block i runs while block i+1 is on
   // its way in and block i-1 on its way out (PCIe is full duplex), on three private streams joined before returning.
   // Row blocks are independent GEMMs (C_i = A_i * B), so the result does not depend on the blocking.
-  const bool pipelined = M >= kHostBlocks * 256 && (a_bytes + c_bytes) >= (size_t(8) << 20) &&
+  // Blocks of >= 512 rows (a GEMM of fewer rows under-fills the device), at most kHostBlocks of them: the tail that
+  // nothing overlaps — the last block's GEMM and copy out — shrinks with the block size.
+  const int blocks = std::min(kHostBlocks, M / 512);
+  const bool pipelined = blocks >= 2 && (a_bytes + c_bytes) >= (size_t(8) << 20) &&
                          !(std::getenv("B200_HGEMM_HOST_UNPIPELINED"));
   if (!pipelined) {
     if ((e = cudaMemcpyAsync(dA, hA, a_bytes, cudaMemcpyHostToDevice, 0)) != cudaSuccess) return int(e);
@@ -251,12 +254,11 @@ int b200_hgemm_host(int acc_bits, const void* hA, const void* hB_kmajor, void* h
   }
   // work queued by the caller on the legacy default stream (non-blocking streams do not wait for it on their own)
   if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return int(e);
-  // A's first block leaves before B so that the link is busy from the first microsecond; the first GEMM needs both
-  const int rows_per = ((M + kHostBlocks - 1) / kHostBlocks + 127) / 128 * 128;   // whole 128-row tiles per block
+  const int rows_per = ((M + blocks - 1) / blocks + 127) / 128 * 128;   // whole 128-row tiles per block
   if ((e = cudaMemcpyAsync(dB, hB_kmajor, b_bytes, cudaMemcpyHostToDevice, ctx.in)) != cudaSuccess) return int(e);
   if ((e = cudaEventRecord(ctx.b_in, ctx.in)) != cudaSuccess) return int(e);
   if ((e = cudaStreamWaitEvent(ctx.run, ctx.b_in, 0)) != cudaSuccess) return int(e);
-  for (int i = 0; i < kHostBlocks; ++i) {
+  for (int i = 0; i < blocks; ++i) {
     const int r0 = i * rows_per, rows = std::min(rows_per, M - r0);
     if (rows <= 0) break;
     const size_t a_off = size_t(r0) * K * 2, c_off = size_t(r0) * N * 2;

@@ -75,11 +75,33 @@ def default_group_m(config_id: int) -> int:
     return 8 if config_table()[config_id]["cta_group"] == 2 else 16
 
 
+def merge_with_current(best: dict) -> None:
+    """Shapes / accumulators a tuning run did not cover keep their entry of the current table (a partial re-tune — one
+    accumulator, one size class — must not erase the rest)."""
+    pat = re.compile(r"\{(\d+), (\d+), (\d+), (-?\d+), (-?\d+), (-?\d+), (-?\d+), (-?\d+), (-?\d+)\}")
+    if not OUT.exists():
+        return
+    for m in pat.finditer(OUT.read_text()):
+        v = [int(x) for x in m.groups()]
+        key = tuple(v[:3])
+        if key == (0, 0, 0):
+            continue
+        for acc, (c, g, sp) in ((32, v[3:6]), (16, v[6:9])):
+            if c >= 0 and acc not in best[key]:
+                best[key][acc] = (c, g, sp, float("nan"), float("nan"))
+
+
 def main(argv):
     if len(argv) < 2:
         print(__doc__)
         return 2
+    runtime_out = None
+    if "--runtime-table" in argv:      # also write the text table that B200_HGEMM_TABLE=<file> loads at run time
+        i = argv.index("--runtime-table")
+        runtime_out = Path(argv[i + 1])
+        argv = argv[:i] + argv[i + 2:]
     best = parse(argv[1:])
+    merge_with_current(best)
     rows = []
     wins = {32: [0, 0], 16: [0, 0]}
     for (m, n, k) in sorted(best):
@@ -88,7 +110,7 @@ def main(argv):
         c16, g16, s16 = e.get(16, (-1, 0, 1))[:3]
         rows.append(f"    {{{m}, {n}, {k}, {c32}, {g32}, {s32}, {c16}, {g16}, {s16}}},")
         for acc in (32, 16):
-            if acc in e:
+            if acc in e and e[acc][3] == e[acc][3]:      # measured in this run (kept entries carry NaN)
                 wins[acc][1] += 1
                 wins[acc][0] += e[acc][3] <= e[acc][4]
     text = ("// GENERATED by tools/tune_b200.py — per-shape winners measured on a B200. Do not edit by hand.\n"
@@ -98,6 +120,15 @@ def main(argv):
             f"static const int kNumTuned = {len(rows)};\n")
     OUT.write_text(text)
     print(f"wrote {len(rows)} entries to {OUT}")
+    if runtime_out is not None:
+        lines = ["# M N K cfg32 gm32 splits32 cfg16 gm16 splits16   (B200_HGEMM_TABLE format, tools/tune_b200.py)"]
+        for (m, n, k) in sorted(best):
+            e = best[(m, n, k)]
+            c32, g32, s32 = e.get(32, (-1, 0, 1))[:3]
+            c16, g16, s16 = e.get(16, (-1, 0, 1))[:3]
+            lines.append(f"{m} {n} {k} {c32} {g32} {s32} {c16} {g16} {s16}")
+        runtime_out.write_text("\n".join(lines) + "\n")
+        print(f"wrote {len(lines) - 1} entries to {runtime_out}")
     for acc in (32, 16):
         if wins[acc][1]:
             print(f"acc {acc}: kernel-time <= cuBLAS(GemmEx) on {wins[acc][0]}/{wins[acc][1]} shapes")
