@@ -37,7 +37,11 @@ def parse_args(argv=None):
                         "harness: eval_one_file.sh per shape (--seconds = benchmark seconds, warm-up = half of it)")
     p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
     p.add_argument("--out_dir", default=str(REPO / "eval_results"))
-    p.add_argument("--mode", default="offline", choices=["offline"])
+    p.add_argument("--mode", default="offline", choices=["offline", "server"], help="server: harness engine only (eval_one_file.sh --mode server)")
+    p.add_argument("--target_qps", type=float, default=100.0)
+    p.add_argument("--perf_funcs", default="", help="harness engine: comma list of baselines to time (default all seven; "
+                   "'auto' = the cuBLASLt-auto-tuning pair, which is all the sweep's target needs)")
+    p.add_argument("--tag", default="", help="suffix of the report files, e.g. _harness_sample")
     p.add_argument("--import_wallgrid", default="", help="turn the stdout of a `dev_check wallgrid` run into the CSV reports")
     p.add_argument("--worker", type=int, default=-1, help=argparse.SUPPRESS)
     p.add_argument("--world", type=int, default=0, help=argparse.SUPPRESS)
@@ -66,7 +70,9 @@ def worker(args, rank, world, gpu):
         return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit)
     done = set(farm.load_done([out]))
     if engine_name == "harness":
-        engine = lambda s: farm.run_harness_engine(s, args.acc_precise, args.seconds / 2, args.seconds, gpu, base / "harness")
+        funcs = farm.AUTO_TUNING_PAIR if args.perf_funcs == "auto" else (args.perf_funcs or None)
+        engine = lambda s: farm.run_harness_engine(s, args.acc_precise, args.seconds / 3, args.seconds, gpu, base / "harness",
+                                                   mode=args.mode, target_qps=args.target_qps, perf_funcs=funcs)
     else:
         engine = lambda s: farm.run_wall_engine(s, bits, args.seconds, (warm, bench), gpu)
     return farm.run_partition(rank, mine, engine, out, done)
@@ -80,9 +86,10 @@ def finish(args, world):
     recs = [r for r in recs if r["mnk"] in wanted]
     peak_tf, peak_hbm, src, _ = bench.peaks()
     acc_dir = "F32F16F16F32" if args.acc_precise == "fp32" else "F16F16F16F16"
-    out_csv = Path(args.out_dir) / f"cuda_l2_b200_{acc_dir}_speedup_{args.mode}.csv"
+    out_csv = Path(args.out_dir) / f"cuda_l2_b200_{acc_dir}_speedup_{args.mode}{args.tag}.csv"
     summary = farm.write_reports(recs, out_csv, peak_tf, peak_hbm)
     summary.update({"n_gpus": world, "peak_source": src, "seconds_per_shape": args.seconds, "tune_rounds": args.tune_rounds,
+                    "engine": args.engine, "mode": args.mode,
                     "missing": sorted(wanted - {r["mnk"] for r in recs})[:20]})
     out_csv.with_name(out_csv.stem + "_summary.json").write_text(json.dumps(summary, indent=1))
     print(json.dumps(summary))
