@@ -66,7 +66,7 @@ def parse_args():
     p.add_argument("--cpu_seconds", type=float, default=10.0, help="bound on the cpu_baseline sample")
     p.add_argument("--sustained_seconds", type=float, default=1.0, help="length of the power-capped loop (0 = skip)")
     p.add_argument("--sweep", type=str, default="grid", help="'grid' (1001 shapes), 'none', or a comma list of M_N_K")
-    p.add_argument("--sweep_ms", type=float, default=12.0, help="sampling budget per shape of the sweep leg")
+    p.add_argument("--sweep_ms", type=float, default=25.0, help="sampling budget per shape of the sweep leg")
     p.add_argument("--cpu_threads", type=int, default=0, help="threads of the CPU arms (0 = half the host's logical CPUs)")
     return p.parse_args()
 
@@ -255,7 +255,7 @@ def sweep_cost(shape) -> float:
     """Seconds one shape costs a rank in the sweep leg (sampling budget floor + a handful of calls)."""
     m, n, k = shape
     t = max(2.0 * m * n * k / 1.3e15, 2.0 * (m * k + n * k + m * n) / 5.5e12, 6e-6)
-    return 0.014 + 9 * t
+    return 0.027 + 9 * t
 
 
 def sweep_partition(shapes, world: int):
@@ -410,6 +410,7 @@ def main():
     e1.record()
     barrier()
     launches = capi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None      # the clock record of the region `value` is computed from
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     if dist is not None:
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
@@ -422,6 +423,9 @@ def main():
     sustained = None
     if args.sustained_seconds > 0:
         sus_steps = max(args.steps, int(args.sustained_seconds / max(ms_total / args.steps * 1e-3, 1e-6)))
+        sus_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sus_sampler.start()
         barrier()
         e0.record()
         for i in range(sus_steps):
@@ -430,7 +434,8 @@ def main():
         barrier()
         sus_ms = max_over_ranks(e0.elapsed_time(e1))
         sustained = {"value": flops_step * sus_steps * world / (sus_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "steps": sus_steps,
-                     "ms_per_step": sus_ms / sus_steps, "seconds": sus_ms * 1e-3}
+                     "ms_per_step": sus_ms / sus_steps, "seconds": sus_ms * 1e-3,
+                     "clocks": sus_sampler.stop() if rank == 0 else None}
 
     # ---- end-to-end leg: host buffers through the C ABI, copies inside the timed region
     # host buffers are allocated (and the calls made) from the CPUs local to this rank's GPU — what numactl would do
@@ -449,7 +454,6 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         near_cpus = len(near.cpus) if near.cpus else None
     e2e_value = flops_step * e2e_steps * world / e2e_s * 1e-12
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- BASELINE config 5: the shape sweep sharded over this job's GPUs
     sweep = None
