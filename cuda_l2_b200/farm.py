@@ -193,6 +193,87 @@ def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tu
     return results
 
 
+PY_FUNCS = {"matmul": "matmul", "hgemm_cublas_tn": "cublas_tn", "hgemm_cublas_nn": "cublas_nn",
+            "hgemm_cublaslt_heuristic_tn": "lt_heur_tn", "hgemm_cublaslt_heuristic_nn": "lt_heur_nn",
+            "hgemm_cublaslt_auto_tuning_tn": "lt_auto_tn", "hgemm_cublaslt_auto_tuning_nn": "lt_auto_nn"}
+
+
+def ctypes_harness_functions(acc_precise: str):
+    """The harness's function table (cuda_l2_b200/harness/common.py baseline_table) with the C-ABI libraries behind the
+    names instead of a JIT-built torch extension: ``cuda_l2_b200_<acc>`` -> libb200_hgemm.so, the six library baselines
+    -> libb200_baselines.so, ``matmul`` -> torch.matmul itself. Same signatures, same ``__name__``s, so the harness's own
+    timing code (harness/benchmark.py) runs on them unchanged."""
+    import torch
+
+    from . import capi
+
+    bl = capi.Baselines(acc_precise)
+
+    def named(name, fn):
+        fn.__name__ = name
+        return fn
+    table = {"matmul": torch.matmul}
+    for fam, method in (("hgemm_cublas", bl.cublas), ("hgemm_cublaslt_heuristic", bl.lt_heuristic), ("hgemm_cublaslt_auto_tuning", bl.lt_autotune)):
+        table[f"{fam}_tn"] = named(f"{fam}_tn", lambda a, b, b_col_major, out, _m=method: _m(capi.Baselines.TN, a, b_col_major, out))
+        table[f"{fam}_nn"] = named(f"{fam}_nn", lambda a, b, b_col_major, out, _m=method: _m(capi.Baselines.NN, a, b, out))
+    kernel = named(f"cuda_l2_b200_{acc_precise}", lambda a, b, b_col_major, out: capi.hgemm(a, b_col_major, out, acc_precise))
+    return table, kernel, bl
+
+
+def run_pyharness_worker(rank: int, world: int, acc_precise: str, shapes, warmup_s: float, bench_s: float, gpu: int | None,
+                         out_path: Path, perf_funcs=("matmul",), mode: str = "offline", target_qps: float | None = None,
+                         seed: int = 0) -> list[dict]:
+    """The harness's Python timing loop (harness/benchmark.py timed_loop — fresh torch.randn operands per sample, one copy
+    per function, zero-filled output, wall clock around one synchronised call, offline or server pacing) over this rank's
+    share of ``shapes``, every requested baseline paired with the kernel in turn, all in ONE process: no JIT build and
+    one process start per GPU instead of eight per shape. It is what fills the ``torch.matmul`` column (dev_check
+    cannot call torch) and the server-mode tables. Call inside a process whose CUDA_VISIBLE_DEVICES selects the GPU."""
+    import random
+
+    import numpy as np
+    import torch
+
+    from .harness import benchmark as bm
+    from .harness.common import Padding
+
+    torch.cuda.set_device(0)
+    torch.set_grad_enabled(False)
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    table, kernel, bl = ctypes_harness_functions(acc_precise)
+    mine = partition(shapes, world)[rank]
+    results = []
+    with open(out_path, "a") as out:
+        for (m, n, k) in mine:
+            rec = {"mnk": f"{m}_{n}_{k}", "rank": rank, "ok": True, "engine": "pyharness", "mode": mode}
+            try:
+                ours = []
+                for name in perf_funcs:
+                    if name.startswith("hgemm_cublaslt_auto_tuning"):
+                        bl.lt_autotune_find(bl.TN if name.endswith("_tn") else bl.NN, m, n, k)
+                    # long kernels: at least three samples even when they do not fit the time budget
+                    est = max(2.0 * m * n * k / 1.2e15, 8e-6)
+                    b_s = max(bench_s, 3 * (2 * est + 12 * (m * k + k * n + m * n) * 2 / 4e12))
+                    _, records = bm.timed_loop(perf_func_list=[table[name], kernel], m=m, n=n, k=k, acc_precise=acc_precise,
+                                               device_type="b200", padding=Padding(), warmup_seconds=warmup_s,
+                                               benchmark_seconds=b_s, target_qps=target_qps if mode == "server" else None)
+                    merged = bm.summarise_records(records, [table[name].__name__, kernel.__name__])
+                    key = PY_FUNCS[name]
+                    rec[key] = merged[table[name].__name__]
+                    rec[key + "_speedup"] = merged[kernel.__name__] / merged[table[name].__name__]
+                    rec[key + "_n"] = merged["samples"]
+                    ours.append(merged[kernel.__name__])
+                rec["ours"] = sum(ours) / len(ours)
+                if "lt_auto_tn_speedup" in rec and "lt_auto_nn_speedup" in rec:
+                    rec["speedup_vs_lt_auto_max"] = min(rec["lt_auto_tn_speedup"], rec["lt_auto_nn_speedup"])
+            except Exception as e:  # keep the sweep alive
+                rec = {"mnk": f"{m}_{n}_{k}", "rank": rank, "ok": False, "error": str(e)[:500]}
+            results.append(rec)
+            out.write(json.dumps(rec) + "\n")
+            out.flush()
+    bl.close()
+    return results
+
+
 def run_partition(rank: int, shapes, engine, out_path: Path | None = None, done: set | None = None) -> list[dict]:
     """Evaluate this rank's share with ``engine(shape) -> dict``; append each result to ``out_path`` (JSONL) so an
     interrupted sweep resumes where it stopped. A failing shape is recorded, not fatal (per-shape isolation)."""

@@ -31,16 +31,20 @@ def parse_args(argv=None):
     p.add_argument("--tune_rounds", default="10,30", help="cuBLASLt auto-tuning warm-up,timed rounds (reference: 50,100)")
     p.add_argument("--shapes", default="grid", help="'grid' (1000 + 2048_11008_4096) or a comma list of M_N_K")
     p.add_argument("--limit", type=int, default=0, help="evaluate only the first N shapes (per GPU for the wallgrid engine)")
-    p.add_argument("--engine", default="auto", choices=["auto", "wallgrid", "wall", "harness"],
+    p.add_argument("--engine", default="auto", choices=["auto", "wallgrid", "wall", "harness", "pyharness"],
                    help="wallgrid: one dev_check process per GPU walks its share (default for --shapes grid); "
                         "wall: one dev_check process per shape (resumable, any shape list); "
-                        "harness: eval_one_file.sh per shape (--seconds = benchmark seconds, warm-up = half of it)")
+                        "harness: eval_one_file.sh per shape (--seconds = benchmark seconds, warm-up = a third of it); "
+                        "pyharness: the harness's Python timing loop in one process per GPU on the C-ABI libraries "
+                        "(--perf_funcs, default matmul: fills the torch.matmul column; server mode supported)")
     p.add_argument("--base_dir", default=str(REPO / "gpurun_out" / "farm"))
     p.add_argument("--out_dir", default=str(REPO / "eval_results"))
     p.add_argument("--mode", default="offline", choices=["offline", "server"], help="server: harness engine only (eval_one_file.sh --mode server)")
     p.add_argument("--target_qps", type=float, default=100.0)
     p.add_argument("--perf_funcs", default="", help="harness engine: comma list of baselines to time (default all seven; "
                    "'auto' = the cuBLASLt-auto-tuning pair, which is all the sweep's target needs)")
+    p.add_argument("--merge_matmul", default="", help="base_dir of a pyharness run whose torch.matmul pair fills that column of this report")
+    p.add_argument("--finish_only", action="store_true", help="write the reports from existing worker_*.jsonl files")
     p.add_argument("--tag", default="", help="suffix of the report files, e.g. _harness_sample")
     p.add_argument("--import_wallgrid", default="", help="turn the stdout of a `dev_check wallgrid` run into the CSV reports")
     p.add_argument("--worker", type=int, default=-1, help=argparse.SUPPRESS)
@@ -69,6 +73,15 @@ def worker(args, rank, world, gpu):
     if engine_name == "wallgrid":
         return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit)
     done = set(farm.load_done([out]))
+    if engine_name == "pyharness":
+        names = [x for x in (args.perf_funcs or "matmul").split(",") if x]
+        if args.perf_funcs == "auto":
+            names = farm.AUTO_TUNING_PAIR.split(",")
+        if gpu is not None:
+            os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu)       # before the first CUDA call of this worker process
+        out = base / f"worker_{args.acc_precise}_{rank}.jsonl"
+        return farm.run_pyharness_worker(rank, world, args.acc_precise, shape_list(args), args.seconds / 4, args.seconds, gpu, out,
+                                         perf_funcs=names, mode=args.mode, target_qps=args.target_qps)
     if engine_name == "harness":
         funcs = farm.AUTO_TUNING_PAIR if args.perf_funcs == "auto" else (args.perf_funcs or None)
         engine = lambda s: farm.run_harness_engine(s, args.acc_precise, args.seconds / 3, args.seconds, gpu, base / "harness",
@@ -84,6 +97,12 @@ def finish(args, world):
     recs = list(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))).values())
     wanted = {"_".join(map(str, s)) for s in (farm.grid_shapes() if args.shapes == "grid" else shape_list(args))}
     recs = [r for r in recs if r["mnk"] in wanted]
+    if args.merge_matmul:      # the torch.matmul column comes from a pyharness run (dev_check cannot call torch)
+        extra = farm.load_done(sorted(Path(args.merge_matmul).glob(f"worker_{args.acc_precise}_*.jsonl")))
+        for r in recs:
+            if r["mnk"] in extra and extra[r["mnk"]].get("matmul_speedup"):
+                r["matmul"] = r["ours"] / extra[r["mnk"]]["matmul_speedup"]     # the pair's own speed-up, on this record's scale
+    recs = [r for r in recs if "speedup_vs_lt_auto_max" in r]
     peak_tf, peak_hbm, src, _ = bench.peaks()
     acc_dir = "F32F16F16F32" if args.acc_precise == "fp32" else "F16F16F16F16"
     out_csv = Path(args.out_dir) / f"cuda_l2_b200_{acc_dir}_speedup_{args.mode}{args.tag}.csv"
@@ -108,6 +127,9 @@ def main(argv=None):
                     rec = farm.parse_wall_line(line)
                     rec.update(mnk=f"{rec['m']}_{rec['n']}_{rec['k']}", rank=0, ok=True)
                     f.write(json.dumps(rec) + "\n")
+        finish(args, args.gpus or 1)
+        return 0
+    if args.finish_only:
         finish(args, args.gpus or 1)
         return 0
     if "RANK" in os.environ and args.worker < 0:          # under torchrun: one rank per GPU

@@ -90,3 +90,22 @@ def test_farm_harness_engine_runs_eval_one_file_for_a_shape(tmp_path):
     assert (tmp_path / "summaries" / "256_512_1024_fp32_offline.json").exists()
     row = farm.speedup_row("256_512_1024", rec)
     assert row["cuBLASLt-auto-tuning-max"] == pytest.approx(rec["speedup_vs_lt_auto_max"]) and row["cuBLAS-max"] == ""
+
+
+def test_pyharness_engine_times_torch_matmul_and_the_library_pairs(tmp_path):
+    """The harness's Python timing loop on the C-ABI libraries (no JIT build): every requested baseline paired with the
+    kernel, offline and server pacing, records in the sweep's schema (this is what fills the torch.matmul column)."""
+    from cuda_l2_b200 import farm
+    out = tmp_path / "worker_fp32_0.jsonl"
+    shapes = [(256, 512, 1024), (64, 4096, 64)]
+    recs = farm.run_pyharness_worker(0, 1, "fp32", shapes, 0.05, 0.2, None, out,
+                                     perf_funcs=("matmul", "hgemm_cublaslt_auto_tuning_tn", "hgemm_cublaslt_auto_tuning_nn"))
+    assert len(recs) == 2 and all(r["ok"] for r in recs), recs
+    for r in recs:
+        assert r["ours"] > 0 and r["matmul"] > 0 and r["lt_auto_tn"] > 0 and r["lt_auto_nn"] > 0
+        assert r["speedup_vs_lt_auto_max"] == min(r["lt_auto_tn_speedup"], r["lt_auto_nn_speedup"])
+        assert farm.speedup_row(r["mnk"], r)["torch.matmul"] == pytest.approx(r["ours"] / r["matmul"])
+    srv = farm.run_pyharness_worker(0, 1, "fp32", shapes[:1], 0.05, 0.3, None, tmp_path / "srv.jsonl",
+                                    perf_funcs=("hgemm_cublaslt_auto_tuning_tn",), mode="server", target_qps=200)
+    assert srv[0]["ok"] and 5 <= srv[0]["lt_auto_tn_n"] <= 200      # ~60 samples at 200 requests/s for 0.3 s
+    assert len(farm.load_done([out])) == 2
