@@ -314,8 +314,8 @@ def run_sweep(args, capi, rank: int, world: int, dist) -> dict | None:
     mine_report = {"rank": rank, "shapes": len(recs), "device_s": dev_s, "leg_s": leg_s, "launches": launches,
                    "flops": sum(2.0 * r[0] * r[1] * r[2] for r in recs), "recs": recs}
     if dist is not None:
-        bucket = [None] * world if rank == 0 else None
-        dist.gather_object(mine_report, bucket, dst=0)
+        bucket = [None] * world
+        dist.all_gather_object(bucket, mine_report)      # a few KB of Python numbers; the GEMM path itself has no collective
     else:
         bucket = [mine_report]
     if rank != 0:
