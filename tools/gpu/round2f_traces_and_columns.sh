@@ -20,6 +20,12 @@ for spec in "2 1024 1024 2048 0" "12 256 2048 2048 0" "1 512 2048 1024 0" "3 409
   set -- $spec
   run $DC time 32 $1 $2 $3 $4 200 $5; run $DE time 32 $1 $2 $3 $4 200 $5; run $DS time 32 $1 $2 $3 $4 200 $5
 done
+echo "== 2c. try_wait suspend hint (20 us): sustained throughput, ours normal / hint build" >> $LOG
+DH=cuda_l2_b200/lib/dev_check_hint
+for spec in "26 8192 8192 8192 8" "3 4096 4096 4096 8" "3 2048 11008 4096 8"; do
+  set -- $spec
+  run $DC sustain 32 $1 $2 $3 $4 1.5 $5 1; run $DH sustain 32 $1 $2 $3 $4 1.5 $5 1
+done
 echo "== 3. bench.py" >> $LOG
 timeout 600 python bench.py --steps 20 --warmup 3 --cpu_seconds 2 > gpurun_out/bench_r2f_20.json 2>> $LOG; tail -c 1500 gpurun_out/bench_r2f_20.json >> $LOG
 echo "== 4. torch.matmul column (pyharness, whole grid, 0.1 s per shape)" >> $LOG
@@ -27,4 +33,4 @@ rm -rf gpurun_out/farm_matmul_fp32
 timeout 900 python farm_sweep.py --gpus 1 --acc_precise fp32 --engine pyharness --perf_funcs matmul --seconds 0.1 \
     --base_dir gpurun_out/farm_matmul_fp32 --out_dir gpurun_out/eval_matmul >> $LOG 2>&1; echo "matmul rc=$?" >> $LOG
 wc -l gpurun_out/farm_matmul_fp32/*.jsonl >> $LOG
-grep -E "FAIL|exit|watchdog|TIME|TRACE|pytest rc|passed|failed|matmul rc|median" $LOG | cut -c1-260 | tail -150
+grep -E "FAIL|exit|watchdog|TIME|TRACE|SUSTAIN|pytest rc|passed|failed|matmul rc|median" $LOG | cut -c1-260 | tail -150
