@@ -376,7 +376,16 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
     int best_c = -1, best_g = 0, best_s = 1; float best_t = 1e30f;
     struct Cand { int c, gm, sp; std::vector<float> t; };
     std::vector<Cand> all;
+    // B200_TUNE_CFGS="3,26,27": only these configurations are candidates (a focused pass over one size class);
+    // B200_TUNE_KEEP_ALL=1: the wall-metric mode ranks every candidate instead of a shortlist
+    static const std::vector<int> only_cfgs = [] {
+      std::vector<int> v;
+      if (const char* e = getenv("B200_TUNE_CFGS")) { for (const char* q = e; *q;) { v.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; } }
+      return v;
+    }();
+    static const bool keep_all = getenv("B200_TUNE_KEEP_ALL") != nullptr;
     for (int c = 0; c < ncfg; ++c) {
+      if (!only_cfgs.empty() && std::find(only_cfgs.begin(), only_cfgs.end(), c) == only_cfgs.end()) continue;
       int bn, st_, cg, cm, cn; b200_hgemm_config_info(c, &bn, &st_, &cg); b200_hgemm_config_cluster(c, &cm, &cn);
       const int mr = b200_hgemm_config_m_rep(c);
       if ((p.M + 127) / 128 < cg * cm * mr || (p.N + bn - 1) / bn < cn) continue;   // part of the tile would only see padding
@@ -464,7 +473,7 @@ static int do_grid(int acc, int part, int nparts, double budget_ms, double min_g
         // GPC layout of the individual GPU (round 2: configurations 18/19 ranked first on the tuning box and lost 8-10 %
         // on the sweep's box), so the table must always have a portable alternative to compare against
         const bool want_plain = !mcast && plain_kept < 3;
-        if (keep.size() < 6 || (cg == 2 && !have_cfg(cd.c) && median(cd.t) <= 1.08f * median(all[0].t)) || want_plain) {
+        if (keep_all || keep.size() < 6 || (cg == 2 && !have_cfg(cd.c) && median(cd.t) <= 1.08f * median(all[0].t)) || want_plain) {
           keep.push_back(cd);
           if (!mcast) ++plain_kept;
         }

@@ -28,26 +28,31 @@ OUT = REPO / "cuda_l2_b200" / "csrc" / "hgemm_tuned_table.inc"
 
 
 def parse(paths):
-    """(m,n,k) -> {acc: (cfg, gm, splits, us, cublas_us)}. A shape measured in several files (repeated tuning runs)
-    is judged on all of them: a candidate's time is the one whose rate is the mean of its rates, and a candidate
-    missing from some run only competes where it was measured at least as often as the winner of that count."""
-    cand_rates = defaultdict(lambda: defaultdict(list))      # (acc,m,n,k) -> (cfg,gm,sp) -> [1/us, ...]
-    cublas_rates = defaultdict(list)
+    """(m,n,k) -> {acc: (cfg, gm, splits, us, cublas_us)}. A shape measured in several files (repeated tuning runs on
+    different boxes, passes with different candidate sets) is judged on all of them: within a file a candidate is
+    scored RELATIVE to the library call measured in the same rotation (cuBLAS time / candidate time — boxes and power
+    states differ by several per cent, the ratio inside one rotation does not), its score is the mean of those ratios,
+    and a candidate seen in fewer files than another gives up 1 % per missing file (less evidence)."""
+    cand_ratio = defaultdict(lambda: defaultdict(list))      # (acc,m,n,k) -> (cfg,gm,sp) -> [cublas_us / us, ...]
+    cublas_us = defaultdict(list)
     for path in paths:
         for line in Path(path).read_text().splitlines():
             if not line.startswith("GRID,"):
                 continue
             f = line.split(",")
             key = (int(f[1]), int(f[2]), int(f[3]), int(f[4]))
-            cublas_rates[key].append(1.0 / float(f[5]))
+            blas = float(f[5])
+            cublas_us[key].append(blas)
             for tok in f[10:]:
                 c, g, sp, us = tok.split(":")
-                cand_rates[key][(int(c), int(g), int(sp))].append(1.0 / float(us))
+                cand_ratio[key][(int(c), int(g), int(sp))].append(blas / float(us))
     best = defaultdict(dict)
-    for key, table in cand_rates.items():
+    for key, table in cand_ratio.items():
         acc, m, n, k = key
-        most = max(len(v) for v in table.values())
-        cands = sorted((len(v) / sum(v), c, g, sp) for (c, g, sp), v in table.items() if len(v) == most)
+        files = len(cublas_us[key])
+        cb = sum(cublas_us[key]) / files
+        # equivalent time on the scale of the mean library time; smaller is better
+        cands = sorted((cb / (sum(v) / len(v)) * (1.0 + 0.01 * (files - len(v))), c, g, sp) for (c, g, sp), v in table.items())
         us, c, g, sp = cands[0]
         # portability guard: a multicast-cluster configuration must beat the best configuration without one by more than
         # 3 % — its performance depends on the GPC layout of the individual GPU (round 2: 18/19 ranked first on the tuning
@@ -61,8 +66,7 @@ def parse(paths):
             if sp2 == 1 and g2 in (0, default_group_m(c2)) and us2 <= us * 1.015 and (not is_multicast(c2) or is_multicast(c)):
                 us, c, g, sp = us2, c2, g2, sp2
                 break
-        cb = cublas_rates[key]
-        best[(m, n, k)][acc] = (c, g, sp, us, len(cb) / sum(cb))
+        best[(m, n, k)][acc] = (c, g, sp, us, cb)
     return best
 
 
