@@ -359,15 +359,20 @@ int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
   // grid starts only when all of it fits (other kernels holding SMs delay it instead of starving half of it into
   // the watchdog), and a grid that can never fit is refused with cudaErrorCooperativeLaunchTooLarge, which launch()
   // turns into the undivided schedule. (Cluster split-K needs nothing: a cluster is co-scheduled by the hardware.)
-  if ((KMODE == kWorkspaceSplitK || KMODE == kStreamK) && cooperative_enabled()) {
+  const bool coop = (KMODE == kWorkspaceSplitK || KMODE == kStreamK) && cooperative_enabled();
+  if (coop) {
     attr[na].id = cudaLaunchAttributeCooperative;
     attr[na].val.cooperative = 1;
     ++na;
   }
-  else if (pdl_enabled()) {
-    // programmatic dependent launch: this kernel's prologue may overlap the tail of the stream's previous kernel; the
-    // kernel itself waits (griddepcontrol.wait) before its first global-memory access. Back-to-back GEMMs lose the
-    // 2-3 us of launch + set-up between them; a caller that synchronises after every call sees no difference.
+  // programmatic dependent launch: this kernel's prologue may overlap the tail of the stream's previous kernel; the
+  // kernel itself waits (griddepcontrol.wait) before its first global-memory access. Back-to-back GEMMs lose the
+  // 2-3 us of launch + set-up between them; a caller that synchronises after every call sees no difference.
+  // Together with the cooperative attribute only where the driver accepts the pair (B200_HGEMM_COOP_PDL=1 to try:
+  // the first refusal switches it off for the process).
+  static bool coop_pdl_ok = [] { const char* e = std::getenv("B200_HGEMM_COOP_PDL"); return e && e[0] == '1'; }();
+  const bool pdl = pdl_enabled() && (!coop || coop_pdl_ok);
+  if (pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -376,6 +381,13 @@ int launch_mode(const DeviceInfo& di, const LaunchArgs& a) {
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg, KMODE>, a.ma, a.mb, a.mc, a.M, a.N, a.K, a.group_m,
                                      a.plan.splits, a.plan.sk_tiles, a.ws, a.ctr, a.c, a.hint_a, a.hint_b);
+  if (e != cudaSuccess && coop && pdl && e != cudaErrorCooperativeLaunchTooLarge) {
+    cudaGetLastError();
+    coop_pdl_ok = false;               // the pair of attributes is not accepted here: cooperative only, from now on
+    cfg.numAttrs = na - 1;
+    e = cudaLaunchKernelEx(&cfg, hgemm_tn_kernel<Cfg, KMODE>, a.ma, a.mb, a.mc, a.M, a.N, a.K, a.group_m,
+                           a.plan.splits, a.plan.sk_tiles, a.ws, a.ctr, a.c, a.hint_a, a.hint_b);
+  }
   return e == cudaSuccess ? kOk : int(e);
 }
 
