@@ -163,7 +163,7 @@ def run_harness_engine(shape, acc_precise: str, warmup_s: float, bench_s: float,
 
 
 def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tune_rounds: tuple[int, int],
-                        gpu: int | None, out_path: Path, limit: int = 0) -> list[dict]:
+                        gpu: int | None, out_path: Path, limit: int = 0, shapes_file: str | None = None) -> list[dict]:
     """One process per GPU walks its share of the cost-sorted grid inside ``dev_check wallgrid`` (CUDA/cuBLAS start-up
     and the 20 GB auto-tuning workspace are paid once per GPU instead of once per shape). The share is the
     round-robin deal ``index % world == rank`` of the cost-sorted list — the same rule ``dev_check`` applies."""
@@ -173,6 +173,8 @@ def run_wallgrid_worker(rank: int, world: int, acc_bits: int, seconds: float, tu
     env = dict(os.environ)
     if gpu is not None:
         env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+    if shapes_file:
+        env["B200_WALLGRID_SHAPES"] = str(shapes_file)      # "M N K" lines replace the grid (partial re-sweeps, samples)
     cmd = [str(exe), "wallgrid", str(acc_bits), str(rank), str(world), str(seconds), str(tune_rounds[0]),
            str(tune_rounds[1]), str(limit)]
     results = []

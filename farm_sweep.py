@@ -43,6 +43,9 @@ def parse_args(argv=None):
     p.add_argument("--target_qps", type=float, default=100.0)
     p.add_argument("--perf_funcs", default="", help="harness engine: comma list of baselines to time (default all seven; "
                    "'auto' = the cuBLASLt-auto-tuning pair, which is all the sweep's target needs)")
+    p.add_argument("--shapes_file", default="", help="wallgrid engine: a file of 'M N K' lines instead of the grid")
+    p.add_argument("--merge_from", default="", help="base_dir of an earlier run of the same engine: its records are kept for every "
+                   "shape this run did not measure again (partial re-sweep after a table change)")
     p.add_argument("--merge_matmul", default="", help="base_dir of a pyharness run whose torch.matmul pair fills that column of this report")
     p.add_argument("--finish_only", action="store_true", help="write the reports from existing worker_*.jsonl files")
     p.add_argument("--tag", default="", help="suffix of the report files, e.g. _harness_sample")
@@ -71,7 +74,7 @@ def worker(args, rank, world, gpu):
     out = base / f"worker_{args.acc_precise}_{rank}.jsonl"
     engine_name = args.engine if args.engine != "auto" else ("wallgrid" if args.shapes == "grid" else "wall")
     if engine_name == "wallgrid":
-        return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit)
+        return farm.run_wallgrid_worker(rank, world, bits, args.seconds, (warm, bench), gpu, out, args.limit, args.shapes_file or None)
     done = set(farm.load_done([out]))
     if engine_name == "pyharness":
         names = [x for x in (args.perf_funcs or "matmul").split(",") if x]
@@ -94,8 +97,14 @@ def worker(args, rank, world, gpu):
 def finish(args, world):
     import bench
     base = Path(args.base_dir)
-    recs = list(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))).values())
+    done = {}
+    if args.merge_from:
+        done.update(farm.load_done(sorted(Path(args.merge_from).glob(f"worker_{args.acc_precise}_*.jsonl"))))
+    done.update(farm.load_done(sorted(base.glob(f"worker_{args.acc_precise}_*.jsonl"))))     # this run's records win
+    recs = list(done.values())
     wanted = {"_".join(map(str, s)) for s in (farm.grid_shapes() if args.shapes == "grid" else shape_list(args))}
+    if args.shapes_file and not args.merge_from:
+        wanted = {"_".join(line.split()) for line in Path(args.shapes_file).read_text().splitlines() if line.strip()}
     recs = [r for r in recs if r["mnk"] in wanted]
     if args.merge_matmul:      # the torch.matmul column comes from a pyharness run (dev_check cannot call torch)
         extra = farm.load_done(sorted(Path(args.merge_matmul).glob(f"worker_{args.acc_precise}_*.jsonl")))
