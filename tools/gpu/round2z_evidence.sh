@@ -17,6 +17,13 @@ timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2>> $LOG; echo "bench 
 timeout 900 python bench.py --mnk 8192_8192_8192 --acc fp16 --steps 300 --sweep none > gpurun_out/r2_bench_8192_fp16.json 2>> $LOG
 timeout 900 python bench.py --mnk 2048_11008_4096 --steps 1000 --sweep none > gpurun_out/r2_bench_2048_11008_4096.json 2>> $LOG
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2_bench_reference.json 2>> $LOG
+echo "== 2b. server mode (qps 100) on the stratified sample, both accumulators: the harness's Python loop on the C-ABI libraries" >> $LOG
+for acc in fp32 fp16; do
+  rm -rf gpurun_out/farm_server_$acc
+  timeout 600 python farm_sweep.py --gpus 1 --acc_precise $acc --engine pyharness --perf_funcs auto --mode server --target_qps 100 --seconds 0.4 \
+      --shapes "$(cat profiles/r2_harness_sample_shapes.txt)" --base_dir gpurun_out/farm_server_$acc --out_dir gpurun_out/eval_server --tag _sample >> $LOG 2>&1
+  echo "server $acc rc=$?" >> $LOG
+done
 echo "== 3. ncu launch list of the bench command (serialised, cold-cache: shares only)" >> $LOG
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 20 --warmup 3 --e2e_steps 2 --cpu_seconds 0.5 --sweep none --sustained_seconds 0 > gpurun_out/r2_bench_under_ncu.json 2>> $LOG
