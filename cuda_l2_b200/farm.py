@@ -239,12 +239,13 @@ def run_pyharness_worker(rank: int, world: int, acc_precise: str, shapes, warmup
     from .harness.common import Padding
 
     torch.cuda.set_device(0)
-    torch.set_grad_enabled(False)
     random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
     table, kernel, bl = ctypes_harness_functions(acc_precise)
     mine = partition(shapes, world)[rank]
     results = []
-    with open(out_path, "a") as out:
+    # (no global torch.set_grad_enabled(False) here: the timing functions are @torch.no_grad themselves, and a caller
+    #  in the same process — a test session — must get its autograd state back)
+    with open(out_path, "a") as out, torch.no_grad():
         for (m, n, k) in mine:
             rec = {"mnk": f"{m}_{n}_{k}", "rank": rank, "ok": True, "engine": "pyharness", "mode": mode}
             try:

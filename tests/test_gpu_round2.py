@@ -216,12 +216,14 @@ def test_operator_and_linear_drop_in():
             out = mlp(xin).float()
         tol = 2e-2 if dt == torch.float16 else 1.5e-1
         assert (out - ref).abs().max() <= tol * max(1.0, float(ref.abs().max())), float((out - ref).abs().max())
-    # autograd through the op (fp32 reference with tolerance)
-    xa = torch.randn(64, 256, device="cuda", dtype=torch.half, requires_grad=True)
-    wa = (torch.randn(128, 256, device="cuda", dtype=torch.half) * 0.1).requires_grad_()
-    ops.hgemm(xa, wa).float().square().sum().backward()
-    xr, wr = xa.detach().float().requires_grad_(), wa.detach().float().requires_grad_()
-    (xr @ wr.t()).square().sum().backward()
+    # autograd through the op (fp32 reference with tolerance); explicit enable_grad: harness code run earlier in the same
+    # session may have switched autograd off globally, as the reference's scripts do (benchmarking_utils.py:9)
+    with torch.enable_grad():
+        xa = torch.randn(64, 256, device="cuda", dtype=torch.half, requires_grad=True)
+        wa = (torch.randn(128, 256, device="cuda", dtype=torch.half) * 0.1).requires_grad_()
+        ops.hgemm(xa, wa).float().square().sum().backward()
+        xr, wr = xa.detach().float().requires_grad_(), wa.detach().float().requires_grad_()
+        (xr @ wr.t()).square().sum().backward()
     assert torch.allclose(xa.grad.float(), xr.grad, rtol=3e-2, atol=0.5)
     assert torch.allclose(wa.grad.float(), wr.grad, rtol=3e-2, atol=0.5)
     with pytest.raises(capi.B200HgemmError):
