@@ -1,5 +1,7 @@
 """Developer tools that shape the shipped dispatcher: the tuner's reading of `dev_check grid` output."""
 import importlib.util
+import json
+import sys
 
 from conftest import REPO
 
@@ -30,3 +32,59 @@ def test_tuner_merges_repeated_runs_and_keeps_the_simple_schedule_on_near_ties(t
     assert abs(both[(256, 256, 4096)][32][3] - 2.0 / (1 / 9.0 + 1 / 8.5)) < 1e-9
     assert both[(256, 256, 4096)][16][:3] == (2, 0, 1)
     assert both[(4096, 4096, 4096)][32][:3] == (3, 8, 1)        # measured in one run only: still judged on that run
+
+
+def test_stratified_sample_is_deterministic_and_covers_every_stratum():
+    sys.path.insert(0, str(REPO / "tools"))
+    import sample_shapes as ss
+    a, b = ss.sample(48), ss.sample(48)
+    assert a == b and len(set(a)) == len(a) and 40 <= len(a) <= 56
+    for must in ss.ALWAYS:
+        assert must in a
+    peak_tf, peak_gbs = ss.peaks()
+    strata = {(ss.roofline_class(*s, peak_tf, peak_gbs), ss.k_band(s[2])) for s in a}
+    assert {c for c, _ in strata} == {"launch", "tensor", "hbm"} and len(strata) >= 8
+    assert all(m % 8 == 0 and n % 8 == 0 and k % 8 == 0 for m, n, k in a)
+
+
+def test_sweeps_overrule_the_tuner_only_beyond_the_threshold(tmp_path, monkeypatch):
+    sys.path.insert(0, str(REPO / "tools"))
+    import select_from_sweeps as sel
+    table = tmp_path / "table.inc"
+    table.write_text("static const TunedEntry kTuned[] = {\n    {64, 64, 64, 2, 0, 1, 12, 0, 1},\n    {128, 64, 64, 2, 0, 1, 12, 0, 1},\n"
+                     "    {256, 64, 64, 2, 0, 1, 12, 0, 1},\n    {0, 0, 0, -1, 0, 1, -1, 0, 1},\n};\n")
+    monkeypatch.setattr(sel, "TABLE", table)
+
+    def rec(mnk, cfg, gm, sp, s):
+        return json.dumps({"mnk": mnk, "cfg": cfg, "gm": gm, "splits": sp, "speedup_vs_lt_auto_max": s, "ok": True})
+    inc, ch = tmp_path / "incumbent.jsonl", tmp_path / "challenger.jsonl"
+    inc.write_text("\n".join([rec("64_64_64", 2, 0, 1, 1.00), rec("128_64_64", 2, 0, 1, 0.95), rec("256_64_64", 2, 0, 1, 0.90)]) + "\n")
+    ch.write_text("\n".join([rec("64_64_64", 3, 8, 1, 1.01),        # +1 point: inside the noise band, incumbent stays
+                             rec("128_64_64", 3, 8, 100, 0.99),     # +4 points: overruled
+                             rec("256_64_64", 1, 0, -4, 0.85)]) + "\n")  # worse: stays
+    out = tmp_path / "merged.jsonl"
+    assert sel.main(["select", "32", "0.02", str(inc), str(ch), "--out", str(out)]) == 0
+    text = table.read_text()
+    assert "{64, 64, 64, 2, 0, 1, 12, 0, 1}" in text and "{128, 64, 64, 3, 8, 100, 12, 0, 1}" in text and "{256, 64, 64, 2, 0, 1, 12, 0, 1}" in text
+    assert "{0, 0, 0, -1, 0, 1, -1, 0, 1}" in text and "overruled by harness-protocol sweeps" in text
+    merged = [json.loads(x) for x in out.read_text().splitlines()]
+    assert [m["source"] for m in merged] == ["challenger.jsonl", "incumbent.jsonl", "incumbent.jsonl"]      # sorted by mnk string
+    # fp16 columns are a separate call and untouched here
+    assert sel.main(["select", "16", "0.02", str(inc), str(ch)]) == 0
+    assert "{128, 64, 64, 3, 8, 100, 3, 8, 100}" in table.read_text()
+
+
+def test_engine_comparison_report(tmp_path):
+    sys.path.insert(0, str(REPO / "tools"))
+    import compare_engines as ce
+    lo, hi = ce.wilson(16, 26)
+    assert 0.42 < lo < 0.44 and 0.77 < hi < 0.79
+    px, hs = tmp_path / "proxy", tmp_path / "harness"
+    px.mkdir(); hs.mkdir()
+    shapes = {"64_64_64": (1.10, 1.20), "4096_4096_4096": (0.99, 1.01), "64_16384_16384": (1.05, 0.90)}
+    (px / "worker_fp32_0.jsonl").write_text("".join(json.dumps({"mnk": k, "ok": True, "speedup_vs_lt_auto_max": v[0]}) + "\n" for k, v in shapes.items()))
+    (hs / "worker_fp32_0.jsonl").write_text("".join(json.dumps({"mnk": k, "ok": True, "speedup_vs_lt_auto_max": v[1]}) + "\n" for k, v in shapes.items()))
+    out = tmp_path / "report.md"
+    assert ce.main(["compare", str(px), str(hs), str(out)]) == 0
+    text = out.read_text()
+    assert "| all | 3 |" in text and "| 1/3 |" in text and "2/3" in text       # verdicts agree on one of three, the harness wins two
